@@ -1,0 +1,129 @@
+/* warpstr_b200 -- C ABI of the B200-native WarpSTR caller hot path.
+ *
+ * The reference (fmfi-compbio/warpstr) is pure Python and has no FFI of its own; each
+ * entry point below names the reference interface it replaces (file:line relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes stubs a WarpSTR maintainer would add
+ * to src/caller/wrapper.py to call them.
+ *
+ * Conventions
+ *   - every function returns 0 (WSTR_OK) or a negative WSTR_ERR_* code, never throws;
+ *   - "d_" pointers are CUDA device pointers on the current device (e.g. taken from
+ *     torch.Tensor.data_ptr()); all other pointers are host pointers and are consumed
+ *     before the call returns;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all device work
+ *     is enqueued on it and the call returns without synchronising unless stated;
+ *   - per-read problems are reported in d_status[read] (WSTR_READ_*), the batch goes on.
+ */
+#ifndef WARPSTR_B200_H
+#define WARPSTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSTR_OK 0
+#define WSTR_ERR_INVALID_ARGUMENT (-1)
+#define WSTR_ERR_CUDA (-2)
+#define WSTR_ERR_TOO_MANY_STATES (-3)     /* automaton larger than the widest kernel (512 states) */
+#define WSTR_ERR_UNSUPPORTED (-4)         /* e.g. min_values_per_state outside 2..8 */
+#define WSTR_ERR_WORKSPACE_TOO_SMALL (-5)
+#define WSTR_ERR_NO_DEVICE (-6)
+
+/* d_status values */
+#define WSTR_READ_OK 0
+#define WSTR_READ_TOO_SHORT 1             /* T <= min_values_per_state: reference raises IndexError (caller.py:206-208) */
+#define WSTR_READ_BACKTRACK 2             /* reference: RuntimeError('Unexpected error during backtracking'), caller.py:290-291 */
+#define WSTR_READ_NO_REPEAT_STATE 3       /* reference: IndexError from trues[0], caller.py:383-384 */
+#define WSTR_READ_SPLINE 4                /* reference: FITPACK error / too few points, caller.py:311 */
+#define WSTR_READ_SPLINE_KNOTS 5          /* smoothing spline needs interior knots: evaluate this read on the host */
+#define WSTR_READ_SEGMENT 6               /* reference: IndexError inside mask_bad_repeats, caller.py:336,358-361,393-411 */
+
+typedef struct wstr_automaton wstr_automaton;
+
+/* ---- library ------------------------------------------------------------------------- */
+int wstr_version(void);
+const char *wstr_error_string(int code);
+/* last CUDA error text seen by this thread (empty string if none) */
+const char *wstr_last_cuda_error(void);
+
+/* ---- (1) expected-signal generation -------------------------------------------------------
+ * Replaces PoreModel.get_value (src/squiggler/pore_model.py:45-47) applied to every sliding
+ * k-mer of a sequence, i.e. Squiggler._generate_signal (src/squiggler/Squiggler.py:20-28).
+ * d_seq: n ASCII bases; d_table: 4^k normalised levels in lexicographic ACGT order;
+ * d_out: n-k+1 levels.  *d_bad is incremented for every k-mer containing a non-ACGT base
+ * (its output is NaN); the reference raises IndexError for such a k-mer. */
+int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d_table, int32_t k,
+                     double *d_out, int32_t *d_bad, void *stream);
+
+/* ---- (2) per-read normalisation -----------------------------------------------------------
+ * Replaces Fast5.get_data_processed (src/schemas/fast5.py:45-57): whole-read spike removal
+ * (brute_remove :90-101, or medfilt 3/5 :72-75, or none) followed by normalize_signal_mad
+ * (:104-114) and the [l_start_raw, r_end_raw] slice.
+ * d_raw: concatenated int16 reads, read r = d_raw[raw_off[r] .. raw_off[r+1]);
+ * spike_mode: 0 None, 1 Brute, 3 median3, 5 median5;
+ * window [win_lo[r], win_hi[r]] (inclusive, as in the reference) is written to
+ * d_out + out_off[r] as float64.  d_shift_scale (optional, may be NULL) receives
+ * {shift, scale} per read.  d_workspace: wstr_normalize_workspace_bytes(n_reads) bytes. */
+int64_t wstr_normalize_workspace_bytes(int32_t n_reads);
+int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off, const int32_t *win_lo,
+                         const int32_t *win_hi, int32_t n_reads, int32_t spike_mode,
+                         double *d_out, const int64_t *out_off, double *d_shift_scale,
+                         void *d_workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- (3) DTW state automaton ----------------------------------------------------------------
+ * wstr_automaton_create uploads one strand's automaton: the flat form of StateAutomata
+ * (src/caller/automata.py:36-48).  All arrays are host pointers.
+ *   values[S]   State.value             seq_idx[S]  State.seq_idx
+ *   in_ptr[S+1], in_idx[E]              CSR of State.incoming, order preserved
+ *   rep_mask[S] StateAutomata.mask      last_base[S] last character of State.kmer
+ *   endstate    StateAutomata.endstate  flank_length Locus.flank_length
+ *   min_values_per_state                tr_calling_config.min_values_per_state (2..8)
+ */
+int wstr_automaton_create(const double *values, const int32_t *seq_idx, const int32_t *in_ptr,
+                          const int32_t *in_idx, const uint8_t *rep_mask, const uint8_t *last_base,
+                          int32_t n_states, int32_t endstate, int32_t flank_length,
+                          int32_t min_values_per_state, wstr_automaton **out);
+int wstr_automaton_destroy(wstr_automaton *a);
+/* info[0]=states per lane (K), info[1]=32-bit direction words per lane per row,
+ * info[2]=edges that are not register-chained, info[3]=slots that carry such edges,
+ * info[4]=n_states, info[5]=n_edges, info[6]=slots with a broken chain */
+int wstr_automaton_info(const wstr_automaton *a, int32_t *info, int32_t n_info);
+/* state index stored at each of the 32*K kernel positions (-1 = padding); for tests */
+int wstr_automaton_layout(const wstr_automaton *a, int32_t *state_of_pos, int32_t n_pos);
+
+/* Bytes of device workspace wstr_warp_batch / wstr_call_batch need to process all reads in
+ * one wave.  A smaller workspace is legal (>= the value returned for the single largest read
+ * plus metadata): the batch is then processed in several waves. */
+int64_t wstr_warp_workspace_bytes(wstr_automaton *const *automata, int32_t n_automata,
+                                  const int32_t *read_automaton, const int32_t *lengths,
+                                  int32_t n_reads);
+
+/* One DP pass + traceback per read.  Replaces WarpSTR.warp (src/caller/caller.py:189-193) =
+ * _calc_dtw_astates (:198-245) + _backtracking (:247-301), for a batch.
+ *   d_signal     float64 samples; read r = d_signal[sig_off[r] .. sig_off[r]+lengths[r]);
+ *                sig_off[r] must be even (16-byte aligned) and the buffer readable one
+ *                element past an odd-length read;
+ *   d_maskbits   NULL for the first pass, else bit t of read r (bit (t&31) of word
+ *                mask_off[r] + (t>>5)) set = badmask[t] (dwell min_values_per_state-1 allowed);
+ *   d_trace      int32 state index per sample, same offsets as d_signal (WarpResult.trace);
+ *   d_end_cost   optional (NULL ok): D[T-1, endstate] per read;
+ *   d_status     int32 per read.
+ */
+int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automata,
+                    const int32_t *read_automaton, const double *d_signal, const int64_t *sig_off,
+                    const int32_t *lengths, const uint32_t *d_maskbits, const int64_t *mask_off,
+                    int32_t n_reads, void *d_workspace, int64_t workspace_bytes,
+                    int32_t *d_trace, double *d_end_cost, int32_t *d_status, void *stream);
+
+/* ---- measurement helper ---------------------------------------------------------------------
+ * Times a dependent-free stream of FP64 adds on every SM (the pipe the DP is bound by) and
+ * returns the achieved rate in 1e12 DADD/s (lane operations); used by bench.py as the
+ * measured roofline denominator.  Synchronises. */
+int wstr_measure_fp64_add_rate(double *tera_adds_per_s, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WARPSTR_B200_H */

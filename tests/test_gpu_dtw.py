@@ -1,0 +1,120 @@
+"""GPU parity of the DP fill + traceback (wstr_warp_batch) against the oracle: traces must be
+identical sample by sample (integer output, bit-exact bar), end costs equal to the last bit
+(same float64 additions in the same order)."""
+import numpy as np
+import pytest
+
+from oracle import caller_oracle as co
+from warpstr_b200 import synth
+from warpstr_b200.automata import StateAutomata
+
+pytestmark = pytest.mark.gpu
+
+LOCI = ['AAAT', 'HD', 'FMR1', 'FMR1_MGG', 'DM2', 'CAN', 'RFC1', 'C9ORF72_100']
+
+
+@pytest.fixture(scope='module')
+def engine(built_lib):
+    from warpstr_b200.caller import CallerEngine
+    return CallerEngine()
+
+
+def _setup(engine, name, n, seed, flank=110, noise=0.15):
+    locus = synth.make_locus(name, seed=seed, flank_length=flank)
+    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    ids = [engine.add_automaton(s, flank) for s in stas]
+    reads = synth.make_reads(locus, n, seed=seed + 100, noise=noise)
+    return locus, stas, ids, reads
+
+
+@pytest.mark.parametrize('name', LOCI)
+def test_first_pass_traces_match_oracle(engine, oracle_c, name):
+    locus, stas, ids, reads = _setup(engine, name, 6, seed=5)
+    sigs = [r.signal for r in reads]
+    aut = [ids[int(r.reverse)] for r in reads]
+    traces, costs = engine.warp_batch(sigs, aut, return_end_cost=True)
+    for r, t, c in zip(reads, traces, costs):
+        tb = co.tables_from(stas[int(r.reverse)])
+        m0 = np.zeros(len(r.signal), dtype=bool)
+        want = oracle_c.warp(r.signal, tb, m0, 4, 110)
+        assert np.array_equal(t, want), (name, r.name)
+        D = oracle_c.fill(r.signal, tb, m0, 4, 110)
+        assert c == D[-1, tb.endstate]
+
+
+@pytest.mark.parametrize('name', ['AAAT', 'HD', 'DM2', 'CAN'])
+def test_masked_pass_matches_oracle(engine, oracle_c, name):
+    """Second-pass semantics: rows with mask=True allow dwell mv-1 (caller.py:218,265-268)."""
+    locus, stas, ids, reads = _setup(engine, name, 4, seed=9, noise=0.25)
+    rng = np.random.default_rng(3)
+    sigs, aut, masks = [], [], []
+    for r in reads:
+        m = np.zeros(len(r.signal), dtype=bool)
+        for _ in range(6):                      # a few masked stretches inside the repeat
+            a = int(rng.integers(900, len(m) - 900))
+            m[a:a + int(rng.integers(20, 120))] = True
+        m[rng.integers(0, len(m), 30)] = True   # and isolated rows
+        sigs.append(r.signal); aut.append(ids[int(r.reverse)]); masks.append(m)
+    traces = engine.warp_batch(sigs, aut, masks)
+    for r, t, m in zip(reads, traces, masks):
+        tb = co.tables_from(stas[int(r.reverse)])
+        want = oracle_c.warp(r.signal, tb, m, 4, 110)
+        assert np.array_equal(t, want), (name, r.name)
+
+
+def test_short_flank_and_small_automaton(engine, oracle_c):
+    locus, stas, ids, reads = _setup(engine, 'AAAT', 5, seed=21, flank=30)
+    sigs = [r.signal for r in reads]
+    aut = [ids[int(r.reverse)] for r in reads]
+    traces = engine.warp_batch(sigs, aut)
+    for r, t in zip(reads, traces):
+        tb = co.tables_from(stas[int(r.reverse)])
+        want = oracle_c.warp(r.signal, tb, np.zeros(len(r.signal), dtype=bool), 4, 30)
+        assert np.array_equal(t, want)
+
+
+def test_mixed_loci_one_batch_and_waves(built_lib, oracle_c):
+    """Several automata (different kernel widths) in one call, and a workspace so small that
+    the batch needs several waves."""
+    from warpstr_b200.caller import CallerEngine
+    eng = CallerEngine(workspace_bytes=6 << 20)
+    sigs, aut, want = [], [], []
+    for name in ('HD', 'CAN', 'AAAT'):
+        locus, stas, ids, reads = _setup(eng, name, 5, seed=33)
+        for r in reads:
+            sigs.append(r.signal); aut.append(ids[int(r.reverse)])
+            tb = co.tables_from(stas[int(r.reverse)])
+            want.append(oracle_c.warp(r.signal, tb, np.zeros(len(r.signal), dtype=bool), 4, 110))
+    traces = eng.warp_batch(sigs, aut)
+    for t, w in zip(traces, want):
+        assert np.array_equal(t, w)
+
+
+def test_unreachable_end_and_tiny_reads(engine, oracle_c):
+    """A read far too short to reach the end state: the reference's traceback stays in the
+    end state all the way (every delta is inf/nan)."""
+    locus, stas, ids, reads = _setup(engine, 'AAAT', 1, seed=4)
+    sig = reads[0].signal[:300].copy()
+    a = ids[int(reads[0].reverse)]
+    tb = co.tables_from(stas[int(reads[0].reverse)])
+    t = engine.warp_batch([sig, sig[:5], sig[:37]], [a, a, a])
+    for s, got in zip([sig, sig[:5], sig[:37]], t):
+        want = oracle_c.warp(s, tb, np.zeros(len(s), dtype=bool), 4, 110)
+        assert np.array_equal(got, want)
+    with pytest.raises(IndexError):
+        engine.warp_batch([sig[:4]], [a])
+
+
+def test_full_call_matches_oracle(engine, oracle_c):
+    """Two passes + mid-stage: allele lengths bit-exact, costs to 1e-9 relative (the host
+    mid-stage makes the same numpy/scipy calls, so they are in fact identical)."""
+    for name in ('HD', 'FMR1'):
+        locus, stas, ids, reads = _setup(engine, name, 5, seed=12)
+        res = engine.call_batch([r.signal for r in reads], [ids[int(r.reverse)] for r in reads],
+                                [r.reverse for r in reads])
+        for r, got in zip(reads, res):
+            tb = co.tables_from(stas[int(r.reverse)])
+            want = co.run_read(r.signal, tb, 110, r.reverse, impl='c')
+            assert got.seq == want.seq and got.resc_seq == want.resc_seq
+            assert got.cost == pytest.approx(want.cost, rel=1e-9)
+            assert got.resc_cost == pytest.approx(want.resc_cost, rel=1e-9)

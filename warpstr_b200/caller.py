@@ -1,0 +1,252 @@
+"""Per-read caller: the reference's ``WarpSTR`` seam on top of the batched GPU engine.
+
+Mirrors caller/caller.py of the reference: ``CallerResult`` (:46-51), ``WarpResult``
+(:54-63), ``WarpSTR(flank_length, states, endstate, repeat_mask, out_warp_path, reverse,
+read_name).run(signal) / .warp(signal, mask)`` (:107-193).  The DP fill and traceback of
+both passes run in the CUDA kernels behind ``wstr_warp_batch``; :class:`CallerEngine`
+batches reads so that thousands of them are in flight at once.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib, midstage
+from .config import CallerConfig, RescalerConfig
+from .templates import reverse_complement
+
+
+@dataclass
+class CallerResult:
+    seq: str
+    cost: float
+    resc_seq: str
+    resc_cost: float
+
+
+@dataclass
+class WarpResult:
+    trace: np.ndarray
+
+    @property
+    def state_transitions(self) -> np.ndarray:
+        keep = np.concatenate(([True], self.trace[1:] != self.trace[:-1]))
+        return self.trace[keep]
+
+
+# exception types the reference raises for a read, by d_status code
+_STATUS_ERRORS = {
+    1: (IndexError, 'index out of bounds: signal shorter than min_values_per_state + 1'),
+    2: (RuntimeError, 'Unexpected error during backtracking'),
+}
+
+
+def pack_signals(signals: Sequence[np.ndarray]):
+    """Concatenate reads into one float64 buffer with 16-byte aligned starts.
+    Returns (pinned host tensor, offsets int64[n], lengths int32[n])."""
+    import torch
+    n = len(signals)
+    lengths = np.fromiter((len(s) for s in signals), dtype=np.int32, count=n)
+    padded = (lengths.astype(np.int64) + 1) & ~1
+    offsets = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        offsets[1:] = np.cumsum(padded[:-1])
+    total = int(padded.sum()) + 2
+    host = torch.empty(total, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+    buf = host.numpy()
+    for s, o, ln in zip(signals, offsets, lengths):
+        buf[o:o + ln] = s
+        if ln & 1:
+            buf[o + ln] = 0.0
+    buf[total - 2:] = 0.0
+    return host, offsets, lengths
+
+
+def pack_masks(masks: Sequence[np.ndarray]):
+    """Bit-pack per-read bool masks, 32 rows per little-endian word.
+    Returns (host uint32 array, word offsets int64[n])."""
+    n = len(masks)
+    nwords = np.fromiter(((len(m) + 31) // 32 for m in masks), dtype=np.int64, count=n)
+    offsets = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        offsets[1:] = np.cumsum(nwords[:-1])
+    out = np.zeros(int(nwords.sum()) + 1, dtype=np.uint32)
+    for m, o, w in zip(masks, offsets, nwords):
+        bits = np.packbits(np.asarray(m, dtype=bool), bitorder='little')
+        pad = (-len(bits)) % 4
+        if pad:
+            bits = np.concatenate((bits, np.zeros(pad, dtype=np.uint8)))
+        out[o:o + w] = bits.view('<u4')
+    return out, offsets
+
+
+class CallerEngine:
+    """Batched two-pass WarpSTR caller on one GPU."""
+
+    def __init__(self, caller_config: Optional[CallerConfig] = None,
+                 rescaler_config: Optional[RescalerConfig] = None, device: str = 'cuda',
+                 workspace_bytes: Optional[int] = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.WarpstrError('warpstr_b200 needs a CUDA device (there is no CPU fallback)')
+        _lib.lib()
+        self.cc = caller_config or CallerConfig()
+        self.rc = rescaler_config or RescalerConfig()
+        self.device = torch.device(device)
+        self.workspace_limit = workspace_bytes
+        self.automata: List[_lib.DeviceAutomaton] = []
+        self.tables: List[dict] = []
+        self._ws = None
+
+    # -- automata ------------------------------------------------------------------------
+    def add_automaton(self, sta, flank_length: int) -> int:
+        """Upload one strand's automaton (object with values/seq_idx/in_ptr/in_idx/rep_mask/
+        last_base/endstate, e.g. warpstr_b200.automata.StateAutomata); returns its id."""
+        import torch
+        with torch.cuda.device(self.device):
+            dev = _lib.DeviceAutomaton.from_automaton(sta, flank_length, self.cc.min_values_per_state)
+        self.automata.append(dev)
+        self.tables.append(dict(values=np.asarray(sta.values, dtype=np.float64),
+                                seq_idx=np.asarray(sta.seq_idx), rep_mask=np.asarray(sta.rep_mask, dtype=bool),
+                                last_base=bytes(np.asarray(sta.last_base, dtype=np.uint8)).decode('ascii'),
+                                flank_length=int(flank_length)))
+        return len(self.automata) - 1
+
+    # -- device helpers ---------------------------------------------------------------------
+    def _workspace(self, need: int):
+        import torch
+        limit = self.workspace_limit
+        if limit is None:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            limit = int(free * 0.6) + (self._ws.numel() if self._ws is not None else 0)
+        size = min(need, max(limit, 1 << 20))
+        if self._ws is None or self._ws.numel() < size:
+            self._ws = None
+            self._ws = torch.empty(size, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def warp_batch(self, signals: Sequence[np.ndarray], aut_ids: Sequence[int],
+                   masks: Optional[Sequence[np.ndarray]] = None, return_end_cost: bool = False):
+        """One DP pass + traceback for every read (reference: WarpSTR.warp, caller.py:189-193).
+        Returns the list of traces (int32 state index per sample)."""
+        import torch
+        n = len(signals)
+        if n == 0:
+            return ([], np.zeros(0)) if return_end_cost else []
+        with torch.cuda.device(self.device):
+            host, off, lengths = pack_signals(signals)
+            d_sig = host.to(self.device, non_blocking=True)
+            aut = np.asarray(aut_ids, dtype=np.int32)
+            d_mask, moff = None, None
+            if masks is not None:
+                hm, moff = pack_masks(masks)
+                d_mask = torch.from_numpy(hm.view(np.int32)).to(self.device)
+            need = _lib.warp_workspace_bytes(self.automata, aut, lengths)
+            ws = self._workspace(need)
+            d_trace = torch.empty(d_sig.numel(), dtype=torch.int32, device=self.device)
+            d_status = torch.zeros(n, dtype=torch.int32, device=self.device)
+            d_cost = torch.empty(n, dtype=torch.float64, device=self.device) if return_end_cost else None
+            _lib.warp_batch(self.automata, aut, d_sig, off, lengths, d_mask, moff, ws, d_trace, d_cost, d_status)
+            trace = d_trace.cpu().numpy()
+            status = d_status.cpu().numpy()
+        for r in np.flatnonzero(status):
+            exc, msg = _STATUS_ERRORS.get(int(status[r]), (RuntimeError, f'read failed with status {status[r]}'))
+            raise exc(msg)
+        traces = [trace[o:o + ln] for o, ln in zip(off, lengths)]
+        if return_end_cost:
+            return traces, d_cost.cpu().numpy()
+        return traces
+
+    # -- full two-pass call ----------------------------------------------------------------
+    def decode(self, aut_id: int, runs: midstage.Runs, reverse: bool) -> str:
+        """caller.py:178-187: last base of each run's k-mer, flanks trimmed."""
+        tb = self.tables[aut_id]
+        seq = ''.join(tb['last_base'][s] for s in runs.states)
+        offset = int(tb['seq_idx'][runs.states[0]])
+        F = tb['flank_length']
+        seq = seq[F - offset:-F]
+        return reverse_complement(seq) if reverse else seq
+
+    def call_batch(self, signals: Sequence[np.ndarray], aut_ids: Sequence[int],
+                   reverse: Sequence[bool]) -> List[CallerResult]:
+        """WarpSTR.run for a batch (caller.py:117-149): pass 1 on the GPU, rescale + mask,
+        pass 2 on the GPU, costs and sequences."""
+        signals = [np.ascontiguousarray(s, dtype=np.float64) for s in signals]
+        traces1 = self.warp_batch(signals, aut_ids)
+        first = []
+        for s, a, t in zip(signals, aut_ids, traces1):
+            tb = self.tables[a]
+            first.append(self._after(t, s, tb, False))
+        traces2 = self.warp_batch([p.rescaled for p in first], aut_ids, [p.badmask for p in first])
+        out = []
+        for p1, a, t2, rev in zip(first, aut_ids, traces2, reverse):
+            tb = self.tables[a]
+            p2 = self._after(t2, p1.rescaled, tb, True)
+            out.append(CallerResult(seq=self.decode(a, p1.runs, rev), cost=p1.cost,
+                                    resc_seq=self.decode(a, p2.runs, rev), resc_cost=p2.cost))
+        return out
+
+    def _after(self, trace, x, tb, second):
+        try:
+            return midstage.after_pass(trace, x, tb['values'], tb['rep_mask'], self.cc, self.rc, second)
+        except midstage.ReadError as e:
+            raise e.kind(str(e))
+
+
+_default_engine: Optional[CallerEngine] = None
+
+
+def default_engine(caller_config=None, rescaler_config=None) -> CallerEngine:
+    global _default_engine
+    if _default_engine is None or caller_config is not None or rescaler_config is not None:
+        _default_engine = CallerEngine(caller_config, rescaler_config)
+    return _default_engine
+
+
+class _StatesView:
+    """Flat tables out of a list of State-like objects (kmer, value, seq_idx, idx, incoming)."""
+
+    def __init__(self, states, endstate, repeat_mask):
+        S = len(states)
+        self.values = np.array([s.value for s in states], dtype=np.float64)
+        self.seq_idx = np.array([s.seq_idx for s in states], dtype=np.int32)
+        self.in_ptr = np.zeros(S + 1, dtype=np.int32)
+        idx: List[int] = []
+        for i, s in enumerate(states):
+            idx.extend(p.idx for p in s.incoming)
+            self.in_ptr[i + 1] = len(idx)
+        self.in_idx = np.array(idx, dtype=np.int32)
+        self.rep_mask = np.array(repeat_mask, dtype=np.uint8)
+        self.last_base = np.frombuffer(''.join(s.kmer[-1] for s in states).encode('ascii'), dtype=np.uint8).copy()
+        self.endstate = int(endstate)
+
+
+@dataclass
+class WarpSTR:
+    """Single-read seam with the reference's constructor (caller.py:107-115)."""
+    flank_length: int
+    states: list
+    endstate: int
+    repeat_mask: List[bool]
+    out_warp_path: Optional[str]
+    reverse: bool
+    read_name: str
+    engine: Optional[CallerEngine] = None
+
+    def __post_init__(self):
+        self._engine = self.engine or default_engine()
+        key = (id(self.states), self.flank_length)
+        cache = self._engine.__dict__.setdefault('_seam_cache', {})
+        if key not in cache:
+            cache[key] = self._engine.add_automaton(_StatesView(self.states, self.endstate, self.repeat_mask),
+                                                    self.flank_length)
+        self._aut = cache[key]
+
+    def warp(self, signal: np.ndarray, mask: Optional[List[bool]] = None) -> WarpResult:
+        sig = np.ascontiguousarray(signal, dtype=np.float64)
+        use_mask = mask is not None and len(mask) > 0
+        traces = self._engine.warp_batch([sig], [self._aut], [np.asarray(mask, dtype=bool)] if use_mask else None)
+        return WarpResult(traces[0].astype(int))
+
+    def run(self, signal: np.ndarray) -> CallerResult:
+        return self._engine.call_batch([signal], [self._aut], [self.reverse])[0]

@@ -1,0 +1,463 @@
+// Kernels (1) expected-signal lookup and (2) per-read normalisation, plus the FP64-add
+// rate probe used as the measured roofline denominator.
+//
+// (1) replaces PoreModel.get_value / Squiggler._generate_signal
+//     (reference src/squiggler/pore_model.py:45-47, src/squiggler/Squiggler.py:20-28).
+// (2) replaces Fast5.remove_spikes + normalize_signal_mad + the window slice
+//     (reference src/schemas/fast5.py:45-57, 68-77, 90-114).  Exact: the percentiles and
+//     the MAD are order statistics, obtained from a histogram of the int16 samples rather
+//     than from a sort, and the float formulas follow numpy's (numpy 2.3
+//     lib/_function_base_impl.py: 'linear' virtual index (n-1)*q, _get_indexes, _lerp,
+//     median = mean of the middle one/two).  Compiled with -fmad=false.
+#include <math.h>
+
+#include "wstr_internal.h"
+
+// ------------------------------------------------------------------------------------------
+// (1) pore-model lookup
+// ------------------------------------------------------------------------------------------
+__global__ void pore_lookup_kernel(const uint8_t *__restrict__ seq, int64_t n_out, const double *__restrict__ table,
+                                   int k, double *__restrict__ out, int32_t *bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_out;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t idx = 0;
+        bool ok = true;
+        for (int p = 0; p < k; ++p) {
+            const uint8_t c = seq[i + p];
+            uint32_t code;
+            switch (c) {
+                case 'A': code = 0; break;
+                case 'C': code = 1; break;
+                case 'G': code = 2; break;
+                case 'T': code = 3; break;
+                default: code = 0; ok = false;
+            }
+            idx = idx * 4u + code;
+        }
+        if (ok) {
+            out[i] = __ldg(table + idx);
+        } else {
+            out[i] = __longlong_as_double(0x7ff8000000000000LL);
+            if (bad) atomicAdd(bad, 1);
+        }
+    }
+}
+
+extern "C" int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d_table, int32_t k, double *d_out,
+                                int32_t *d_bad, void *stream) {
+    if (!d_seq || !d_table || !d_out || k < 1 || k > 15) return WSTR_ERR_INVALID_ARGUMENT;
+    const int64_t n_out = n - k + 1;
+    if (n_out <= 0) return WSTR_OK;
+    const int threads = 256;
+    int64_t blocks = (n_out + threads - 1) / threads;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pore_lookup_kernel<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(d_seq, n_out, d_table, k, d_out,
+                                                                                       d_bad);
+    WSTR_CUDA(cudaGetLastError());
+    return WSTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// (2) normalisation
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int NT = 256;              // threads per CTA
+constexpr int PER = 8;               // samples per thread per tile
+constexpr int TILE = NT * PER;       // 2048
+constexpr int HBINS = 8192;          // shared histogram covers values [0, HBINS)
+constexpr int GBINS = 65536;         // global fallback histogram covers every int16
+
+struct NormParams {
+    const int16_t *raw;
+    const int64_t *raw_off;          // device copy, n+1
+    const int32_t *win_lo, *win_hi;  // device copies
+    const int64_t *out_off;          // device copy
+    double *out;
+    double *shift_scale;             // may be NULL
+    uint32_t *ghist;                 // gridDim.x * GBINS, zero on entry and on exit
+    int32_t *queue;
+    int32_t n_reads;
+    int32_t spike_mode;
+};
+
+struct NormSmem {
+    uint32_t hist[HBINS];
+    int16_t tile[TILE + 8];
+    int16_t filt[TILE];
+    uint16_t spikes[TILE];
+    int32_t warp_sums[NT / 32];
+    int32_t n_spikes;
+    int32_t next_read;
+    int32_t vmin, vmax;
+    int32_t ghist_dirty;
+    int32_t ranks_val[6];
+    double shift, scale;
+};
+
+__device__ __forceinline__ uint32_t hcount(const NormSmem &sm, const uint32_t *gh, int v) {
+    if (v >= 0 && v < HBINS) return sm.hist[v];
+    if (v < -32768 || v > 32767) return 0u;
+    return sm.ghist_dirty ? gh[v + 32768] : 0u;
+}
+
+__device__ __forceinline__ int16_t median_small(int16_t *w, int n) {
+    // insertion sort of <= 5 values, then numpy's median (mean of the middle two for even n,
+    // truncated toward zero when stored back into the int16 array: fast5.py:100)
+    for (int a = 1; a < n; ++a) {
+        int16_t key = w[a];
+        int b = a - 1;
+        while (b >= 0 && w[b] > key) {
+            w[b + 1] = w[b];
+            --b;
+        }
+        w[b + 1] = key;
+    }
+    if (n & 1) return w[n / 2];
+    const double mid = ((double)w[n / 2 - 1] + (double)w[n / 2]) / 2.0;
+    return (int16_t)mid;
+}
+
+// warp 0: smallest value v >= vstart with  (count of samples <= v) > rank, scanning 32 bins a step
+__device__ int value_at_rank(const NormSmem &sm, const uint32_t *gh, int64_t rank, int lane) {
+    int64_t cum = 0;
+    for (int base = sm.vmin; base <= sm.vmax; base += 32) {
+        const int v = base + lane;
+        uint32_t c = v <= sm.vmax ? hcount(sm, gh, v) : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, cum + inc > rank);
+        if (hit) return base + (__ffs(hit) - 1);
+        cum += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    return sm.vmax;
+}
+
+// warp 0: the rank-th smallest |v - shift| over all samples (float64, as numpy computes it)
+__device__ double absdev_at_rank(const NormSmem &sm, const uint32_t *gh, double shift, int64_t rank, int lane) {
+    const int fl = (int)floor(shift);
+    int64_t cum = 0;
+    const int span = max(fl - sm.vmin, sm.vmax - (fl + 1)) + 1;
+    for (int base = 0; base < span; base += 32) {
+        const int m = base + lane;
+        const int lo = fl - m, hi = fl + 1 + m;
+        const uint32_t cl = hcount(sm, gh, lo), chh = hcount(sm, gh, hi);
+        uint32_t inc = cl + chh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, cum + inc > rank);
+        if (hit) {
+            const int src = __ffs(hit) - 1;
+            const int64_t before = cum + __shfl_sync(0xffffffffu, (int64_t)inc - (cl + chh), src);
+            const uint32_t scl = __shfl_sync(0xffffffffu, cl, src), sch = __shfl_sync(0xffffffffu, chh, src);
+            const int mm = base + src;
+            const double dl = fabs((double)(fl - mm) - shift), du = fabs((double)(fl + 1 + mm) - shift);
+            // inside the pair the nearer value comes first
+            const int64_t within = rank - before;
+            if (dl <= du) return within < (int64_t)scl ? dl : du;
+            return within < (int64_t)sch ? du : dl;
+        }
+        cum += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    return 0.0;
+}
+
+__global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NormSmem &sm = *reinterpret_cast<NormSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *gh = p.ghist + (size_t)blockIdx.x * GBINS;
+
+    for (;;) {
+        if (tid == 0) sm.next_read = atomicAdd(p.queue, 1);
+        __syncthreads();
+        const int r = sm.next_read;
+        if (r >= p.n_reads) break;
+        const int16_t *raw = p.raw + p.raw_off[r];
+        const int64_t N = p.raw_off[r + 1] - p.raw_off[r];
+        const int64_t lo = p.win_lo[r], hi = p.win_hi[r];
+        const int64_t Tw = hi >= lo ? (min(hi, N - 1) - lo + 1) : 0;     // numpy slice semantics
+        double *out = p.out + p.out_off[r];
+        int16_t *stash = reinterpret_cast<int16_t *>(out) + 3 * Tw;      // tail of the output window
+
+        for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
+        if (tid == 0) {
+            sm.vmin = 32767;
+            sm.vmax = -32768;
+            sm.ghist_dirty = 0;
+        }
+        if (tid < 8) sm.tile[tid] = 0;
+        __syncthreads();
+
+        int lmin = 32767, lmax = -32768;
+        for (int64_t t0 = 0; t0 < N; t0 += TILE) {
+            const int len = (int)min((int64_t)TILE, N - t0);
+            // tile[2 + t] = sample t0 + t; two halo samples on each side
+            for (int t = tid; t < len + 2; t += NT) {
+                const int64_t g = t0 + t;
+                sm.tile[2 + t] = g < N ? raw[g] : (int16_t)0;
+            }
+            if (p.spike_mode != 1 && tid < 2) {   // median filters look at raw neighbours
+                const int64_t g = t0 - 2 + tid;
+                sm.tile[tid] = g >= 0 ? raw[g] : (int16_t)0;
+            }
+            if (tid == 0) sm.n_spikes = 0;
+            __syncthreads();
+
+            if (p.spike_mode == 1) {
+                // Brute (fast5.py:90-101): ordered list of out-of-range samples of this tile ...
+                int cnt = 0;
+                const int base = tid * PER;
+                bool flag[PER];
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int t = base + u;
+                    const int16_t vv = t < len ? sm.tile[2 + t] : (int16_t)500;
+                    flag[u] = (vv > 1000) || (vv < 250);
+                    cnt += flag[u];
+                }
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) sm.warp_sums[warp] = inc;
+                __syncthreads();
+                int woff = 0;
+                for (int w = 0; w < warp; ++w) woff += sm.warp_sums[w];
+                int pos = woff + inc - cnt;
+#pragma unroll
+                for (int u = 0; u < PER; ++u)
+                    if (flag[u]) sm.spikes[pos++] = (uint16_t)(base + u);
+                if (tid == NT - 1) sm.n_spikes = woff + inc;
+                __syncthreads();
+                // ... patched one after the other: later medians see earlier fixes
+                if (tid == 0) {
+                    for (int s = 0; s < sm.n_spikes; ++s) {
+                        const int t = sm.spikes[s];
+                        const int64_t g = t0 + t;
+                        if (g > 2) {
+                            int16_t w5[5];
+                            const int n = (int)min((int64_t)5, N - (g - 2));
+                            for (int u = 0; u < n; ++u) w5[u] = sm.tile[t + u];   // samples g-2 .. g-2+n-1
+                            sm.tile[2 + t] = median_small(w5, n);
+                        }
+                    }
+                }
+                __syncthreads();
+            } else if (p.spike_mode == 3 || p.spike_mode == 5) {
+                // scipy.signal.medfilt: zero-padded running median (fast5.py:72-75)
+                const int h = p.spike_mode / 2;
+                for (int t = tid; t < len; t += NT) {
+                    int16_t w5[5];
+                    for (int u = -h; u <= h; ++u) {
+                        const int64_t g = t0 + t + u;
+                        w5[u + h] = (g >= 0 && g < N) ? sm.tile[2 + t + u] : (int16_t)0;
+                    }
+                    sm.filt[t] = median_small(w5, 2 * h + 1);
+                }
+                __syncthreads();
+                for (int t = tid; t < len; t += NT) sm.tile[2 + t] = sm.filt[t];
+                __syncthreads();
+            }
+
+            // histogram, extrema and the window stash
+            for (int t = tid; t < len; t += NT) {
+                const int vv = sm.tile[2 + t];
+                lmin = min(lmin, vv);
+                lmax = max(lmax, vv);
+                if (vv >= 0 && vv < HBINS) {
+                    atomicAdd(&sm.hist[vv], 1u);
+                } else {
+                    atomicAdd(&gh[vv + 32768], 1u);
+                    sm.ghist_dirty = 1;
+                }
+                const int64_t g = t0 + t;
+                if (g >= lo && g <= hi) stash[g - lo] = (int16_t)vv;
+            }
+            __syncthreads();
+            if (p.spike_mode == 1 && tid < 2) sm.tile[tid] = sm.tile[len + tid];   // patched carry
+            __syncthreads();
+        }
+        atomicMin(&sm.vmin, lmin);
+        atomicMax(&sm.vmax, lmax);
+        __threadfence_block();
+        __syncthreads();
+
+        if (warp == 0 && N > 0) {
+            // np.percentile(data, (46.5, 53.5)), method 'linear'
+            double pr[2];
+            const double qs[2] = {46.5 / 100.0, 53.5 / 100.0};
+            for (int q = 0; q < 2; ++q) {
+                const double vidx = (double)(N - 1) * qs[q];
+                int64_t i0 = (int64_t)floor(vidx), i1 = i0 + 1;
+                if (vidx >= (double)(N - 1)) i0 = i1 = N - 1;
+                const double gamma = vidx - (double)i0;
+                const int a = value_at_rank(sm, gh, i0, lane);
+                const int b = value_at_rank(sm, gh, i1, lane);
+                const int16_t diff16 = (int16_t)(b - a);              // numpy subtracts in int16
+                const double diff = (double)diff16;
+                double res = (double)a + diff * gamma;
+                if (gamma >= 0.5) res = (double)b - diff * (1.0 - gamma);
+                pr[q] = res;
+            }
+            const double shift = (pr[0] + pr[1]) / 2.0;
+            // np.median(np.abs(data - shift))
+            double scale;
+            if (N & 1) {
+                scale = absdev_at_rank(sm, gh, shift, N / 2, lane);
+            } else {
+                const double m1 = absdev_at_rank(sm, gh, shift, N / 2 - 1, lane);
+                const double m2 = absdev_at_rank(sm, gh, shift, N / 2, lane);
+                scale = (m1 + m2) / 2.0;
+            }
+            if (lane == 0) {
+                sm.shift = shift;
+                sm.scale = scale;
+                if (p.shift_scale) {
+                    p.shift_scale[2 * r] = shift;
+                    p.shift_scale[2 * r + 1] = scale;
+                }
+            }
+        }
+        __syncthreads();
+        const double shift = sm.shift, scale = sm.scale;
+
+        // convert the stashed int16 window in place, front to back, one tile at a time
+        for (int64_t t0 = 0; t0 < Tw; t0 += TILE) {
+            const int len = (int)min((int64_t)TILE, Tw - t0);
+            for (int t = tid; t < len; t += NT) sm.filt[t] = stash[t0 + t];
+            __syncthreads();
+            for (int t = tid; t < len; t += NT) out[t0 + t] = ((double)sm.filt[t] - shift) / scale;
+            __syncthreads();
+        }
+        // leave the global fallback histogram clean for the next read
+        if (sm.ghist_dirty) {
+            for (int b = tid; b < GBINS; b += NT) gh[b] = 0u;
+        }
+        __syncthreads();
+    }
+}
+
+int norm_grid(int n_reads) {
+    int g = 148 * 2;
+    return n_reads < g ? (n_reads < 1 ? 1 : n_reads) : g;
+}
+
+}  // namespace
+
+extern "C" int64_t wstr_normalize_workspace_bytes(int32_t n_reads) {
+    if (n_reads < 0) return WSTR_ERR_INVALID_ARGUMENT;
+    const int64_t meta = 256 + ((int64_t)n_reads + 1) * 8 * 2 + (int64_t)n_reads * 4 * 2 + 1024;
+    return meta + (int64_t)norm_grid(n_reads) * GBINS * 4;
+}
+
+extern "C" int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off, const int32_t *win_lo,
+                                    const int32_t *win_hi, int32_t n_reads, int32_t spike_mode, double *d_out,
+                                    const int64_t *out_off, double *d_shift_scale, void *d_workspace,
+                                    int64_t workspace_bytes, void *stream) {
+    if (!d_raw || !raw_off || !win_lo || !win_hi || !d_out || !out_off || !d_workspace || n_reads < 0)
+        return WSTR_ERR_INVALID_ARGUMENT;
+    if (spike_mode != 0 && spike_mode != 1 && spike_mode != 3 && spike_mode != 5) return WSTR_ERR_INVALID_ARGUMENT;
+    if (n_reads == 0) return WSTR_OK;
+    if (workspace_bytes < wstr_normalize_workspace_bytes(n_reads)) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    for (int r = 0; r < n_reads; ++r)
+        if (raw_off[r + 1] <= raw_off[r] || win_lo[r] < 0) return WSTR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(d_workspace);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = (off + bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_q = take(256), o_ro = take(sizeof(int64_t) * (n_reads + 1)), o_oo = take(sizeof(int64_t) * n_reads),
+                 o_lo = take(sizeof(int32_t) * n_reads), o_hi = take(sizeof(int32_t) * n_reads);
+    const int grid = norm_grid(n_reads);
+    const size_t o_gh = take(0);
+    if ((int64_t)(o_gh + (size_t)grid * GBINS * 4) > workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    WSTR_CUDA(cudaMemsetAsync(ws + o_q, 0, 256, s));
+    WSTR_CUDA(cudaMemcpyAsync(ws + o_ro, raw_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, s));
+    WSTR_CUDA(cudaMemcpyAsync(ws + o_oo, out_off, sizeof(int64_t) * n_reads, cudaMemcpyHostToDevice, s));
+    WSTR_CUDA(cudaMemcpyAsync(ws + o_lo, win_lo, sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, s));
+    WSTR_CUDA(cudaMemcpyAsync(ws + o_hi, win_hi, sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, s));
+    WSTR_CUDA(cudaMemsetAsync(ws + o_gh, 0, (size_t)grid * GBINS * 4, s));
+    NormParams p;
+    p.raw = d_raw;
+    p.raw_off = reinterpret_cast<const int64_t *>(ws + o_ro);
+    p.out_off = reinterpret_cast<const int64_t *>(ws + o_oo);
+    p.win_lo = reinterpret_cast<const int32_t *>(ws + o_lo);
+    p.win_hi = reinterpret_cast<const int32_t *>(ws + o_hi);
+    p.out = d_out;
+    p.shift_scale = d_shift_scale;
+    p.ghist = reinterpret_cast<uint32_t *>(ws + o_gh);
+    p.queue = reinterpret_cast<int32_t *>(ws + o_q);
+    p.n_reads = n_reads;
+    p.spike_mode = spike_mode;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WSTR_CUDA(cudaFuncSetAttribute(normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(NormSmem)));
+        attr_set = true;
+    }
+    normalize_kernel<<<grid, NT, sizeof(NormSmem), s>>>(p);
+    WSTR_CUDA(cudaGetLastError());
+    return WSTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 add-rate probe
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_add_probe(double *out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double inc = seed * 0.5;
+    for (int i = 0; i < iters; ++i) {
+        a0 += inc; a1 += inc; a2 += inc; a3 += inc; a4 += inc; a5 += inc; a6 += inc; a7 += inc;
+        a0 += a1;  a2 += a3;  a4 += a5;  a6 += a7;  a1 += inc; a3 += inc; a5 += inc; a7 += inc;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int wstr_measure_fp64_add_rate(double *tera_adds_per_s, void *stream) {
+    if (!tera_adds_per_s) return WSTR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    WSTR_CUDA(cudaGetDevice(&dev));
+    WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double *d = nullptr;
+    WSTR_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, s);
+        fp64_add_probe<<<blocks, threads, 0, s>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(e1, s);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return wstr_set_cuda_error(e, "fp64 probe");
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double adds = (double)blocks * threads * iters * 16.0;
+        const double rate = adds / (ms * 1e-3) / 1e12;
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tera_adds_per_s = best;
+    return WSTR_OK;
+}

@@ -1,0 +1,98 @@
+// Internal structures shared by the host side of the C ABI and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "warpstr_b200.h"
+
+#define WSTR_MAX_K 16            // states per lane in the widest kernel (32*16 = 512 positions)
+#define WSTR_MAX_MV 8
+#define WSTR_SIG_CHUNK 256       // samples per bulk-copied signal tile (2 KB)
+#define WSTR_WARPS_PER_CTA 4
+#define WSTR_XTAB_MAX_ROWS 48    // rows of 32 extra-edge entries kept in shared memory per warp
+#define WSTR_NO_EDGE 0xFFFFu
+
+// Device view of one automaton laid out for the warp-per-read kernel.
+// Position p = lane*K + slot.  A "chain" edge is the edge (p-1 -> p): it is served from
+// registers (same lane) or one shuffle (slot 0).  Every other incoming edge is an "extra":
+// its source publishes its pipeline value to shared memory each row.
+struct DevAutomaton {
+    const double *v_pos;             // [32*K] level per position (0 for padding)
+    const int16_t *state_of_pos;     // [32*K] state index, -1 = padding
+    const uint32_t *lane_bits;       // [32*4]: chain / band / src / real bits per lane (K bits each)
+    const uint16_t *xtab;            // [n_xrows*32] src_pos | before<<15, WSTR_NO_EDGE = none
+    uint8_t xoff[WSTR_MAX_K + 1];    // rows of slot k are xoff[k] .. xoff[k+1]
+    uint8_t pad_[3];
+    int32_t K;                       // slots per lane
+    int32_t W;                       // direction words per lane per row (4 bits per slot)
+    int32_t S;                       // states
+    int32_t n_xrows;
+    int32_t end_pos;                 // position of the end state
+    int32_t mv;                      // min_values_per_state
+    int32_t th1;                     // 6*(flank_length-10)
+    int32_t band6;                   // 6*(flank_length-10) (second threshold = T - band6)
+    int32_t init_pos[WSTR_MAX_MV + 1];  // positions of states 0..mv (row-0 initialisation)
+    uint32_t allchain_slots;         // slot k: every lane's position is chained
+    uint32_t extra_slots;            // slot k has at least one extra edge
+    uint32_t src_slots;              // slot k holds at least one extra-edge source
+};
+
+// Per-read record of one wave.
+struct ReadMeta {
+    int64_t sig_off;     // element offset into the signal buffer
+    int64_t dir_off;     // word offset into the direction-bit workspace
+    int64_t mask_off;    // word offset into maskbits (ignored if maskbits == NULL)
+    int32_t T;
+    int32_t aut;
+    int32_t read;        // index in the caller's arrays (status / end_cost)
+    int32_t pad_;
+};
+
+struct FillParams {
+    const DevAutomaton *auts;
+    const ReadMeta *meta;        // this wave's reads
+    const int32_t *order;        // indices into meta, longest first, for this K class
+    int32_t n;                   // entries in order
+    int32_t *queue;              // work counter (zeroed before launch)
+    const double *signal;
+    const uint32_t *maskbits;    // may be NULL
+    uint32_t *dir;               // direction-bit workspace
+    double *end_cost;            // may be NULL; indexed by ReadMeta.read
+    int32_t *status;             // indexed by ReadMeta.read
+};
+
+struct TraceParams {
+    const DevAutomaton *auts;
+    const ReadMeta *meta;
+    int32_t n;
+    const uint32_t *maskbits;
+    const uint32_t *dir;
+    int32_t *trace;              // same offsets as the signal
+    int32_t *status;
+};
+
+struct wstr_automaton {
+    DevAutomaton dev;            // pointers into d_blob
+    void *d_blob;
+    int32_t n_edges, n_extra, n_extra_slots, n_broken_slots;
+    int32_t flank_length;
+    int32_t *h_state_of_pos;     // host copy, 32*K
+    // tables kept for the mid-stage kernels (device, inside d_blob)
+    const double *d_values;      // [S]
+    const int32_t *d_seq_idx;    // [S]
+    const uint8_t *d_rep_mask;   // [S]
+    const uint8_t *d_last_base;  // [S]
+};
+
+int wstr_set_cuda_error(cudaError_t e, const char *where);
+
+#define WSTR_CUDA(call)                                                   \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return wstr_set_cuda_error(e_, #call);     \
+    } while (0)
+
+// kernels / launchers (dtw.cu)
+int wstr_launch_fill(int K, int mv, const FillParams &p, cudaStream_t s);
+int wstr_launch_traceback(const TraceParams &p, cudaStream_t s);
+int wstr_fill_smem_bytes(int K);
