@@ -86,9 +86,15 @@ int wstr_automaton_create(const double *values, const int32_t *seq_idx, const in
                           int32_t n_states, int32_t endstate, int32_t flank_length,
                           int32_t min_values_per_state, wstr_automaton **out);
 int wstr_automaton_destroy(wstr_automaton *a);
+/* Host-only dry run of the kernel layout (no device needed): info[0]=chain slots per lane (KC),
+ * info[1]=generic slots per lane (KG), info[2]=in-degree the generic slots are unrolled for,
+ * info[3]=lanes holding chains, info[4]=states placed in generic slots; state_of_pos (optional)
+ * receives the state at each of the 32*(KC+KG) positions, -1 = padding. */
+int wstr_automaton_plan(const int32_t *in_ptr, const int32_t *in_idx, int32_t n_states,
+                        int32_t min_values_per_state, int32_t *info, int32_t *state_of_pos, int32_t n_pos);
 /* info[0]=states per lane (K), info[1]=32-bit direction words per lane per row,
- * info[2]=edges that are not register-chained, info[3]=slots that carry such edges,
- * info[4]=n_states, info[5]=n_edges, info[6]=slots with a broken chain */
+ * info[2]=chain slots (KC), info[3]=generic slots (KG), info[4]=n_states, info[5]=n_edges,
+ * info[6]=states placed in generic slots */
 int wstr_automaton_info(const wstr_automaton *a, int32_t *info, int32_t n_info);
 /* state index stored at each of the 32*K kernel positions (-1 = padding); for tests */
 int wstr_automaton_layout(const wstr_automaton *a, int32_t *state_of_pos, int32_t n_pos);

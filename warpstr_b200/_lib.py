@@ -38,6 +38,8 @@ _SIGNATURES = {
                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.POINTER(c_vp)]),
     'wstr_automaton_destroy': (ctypes.c_int, [c_vp]),
+    'wstr_automaton_plan': (ctypes.c_int, [c_i32p, c_i32p, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i32p,
+                                           ctypes.c_int32]),
     'wstr_automaton_info': (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int32]),
     'wstr_automaton_layout': (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int32]),
     'wstr_warp_workspace_bytes': (ctypes.c_int64, [ctypes.POINTER(c_vp), ctypes.c_int32, c_i32p, c_i32p,
@@ -130,8 +132,8 @@ class DeviceAutomaton:
     def info(self) -> dict:
         buf = np.zeros(7, dtype=np.int32)
         check(lib().wstr_automaton_info(self.handle, _ptr(buf, c_i32p), 7), 'wstr_automaton_info')
-        keys = ('states_per_lane', 'dir_words_per_row', 'extra_edges', 'extra_slots', 'n_states', 'n_edges',
-                'broken_chain_slots')
+        keys = ('states_per_lane', 'dir_words_per_row', 'chain_slots', 'generic_slots', 'n_states', 'n_edges',
+                'generic_states')
         return dict(zip(keys, (int(x) for x in buf)))
 
     def layout(self) -> np.ndarray:
@@ -150,6 +152,19 @@ class DeviceAutomaton:
             self.close()
         except Exception:
             pass
+
+
+def automaton_plan(in_ptr, in_idx, n_states: int, min_values_per_state: int = 4):
+    """Host-only dry run of the kernel layout: (info dict, state_of_pos)."""
+    ip = _np(in_ptr, np.int32)
+    ii = _np(in_idx, np.int32)
+    info = np.zeros(5, dtype=np.int32)
+    sop = np.full(32 * 16, -1, dtype=np.int32)
+    check(lib().wstr_automaton_plan(_ptr(ip, c_i32p), _ptr(ii, c_i32p), int(n_states), int(min_values_per_state),
+                                    _ptr(info, c_i32p), _ptr(sop, c_i32p), int(sop.shape[0])), 'wstr_automaton_plan')
+    keys = ('chain_slots', 'generic_slots', 'unrolled_in_degree', 'chain_lanes', 'generic_states')
+    d = dict(zip(keys, (int(x) for x in info)))
+    return d, sop[:32 * (d['chain_slots'] + d['generic_slots'])]
 
 
 def _handles(automata: Sequence[DeviceAutomaton]):

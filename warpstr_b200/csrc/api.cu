@@ -36,88 +36,158 @@ extern "C" const char *wstr_error_string(int code) {
 }
 
 // ------------------------------------------------------------------------------------------
-// automaton layout
+// automaton layout (see dtw.cu)
 //
-// The kernel serves the edge (position p-1 -> position p) from registers; every other edge
-// costs shared-memory traffic and, worse, instructions in every lane of the warp for the
-// slot it lands in.  So: cover the automaton with as few vertex-disjoint paths as possible
-// (greedy, forward edges only), lay the paths end to end, and everything that is not a
-// path edge becomes an "extra".
+// A "chain link" j -> t is an edge where j has no other successor and t no other predecessor.
+// Maximal chains of links (the flanks, mostly) are cut into full lanes of KC states, taken
+// from the chain's end so that the last state of every chain is a lane tail (published);
+// everything else (chain heads that do not fill a lane, the repeat region) becomes a
+// generic state.  Among the (KC, KG) splits the library is built with, the cheapest one
+// that fits is used.
 // ------------------------------------------------------------------------------------------
 namespace {
 
-const int kAllowedK[] = {4, 8, 9, 10, 12, 16};
-
-struct Extra {
-    int src_state;
-    bool before_chain;
+struct Split {
+    int kc, kg;
+    unsigned mv_mask;   // bit mv set = instantiated for that min_values_per_state
 };
+// keep in sync with wstr_launch_fill in dtw.cu
+const Split kSplits[] = {{6, 2, 0x38}, {4, 4, 0x10}, {8, 2, 0x10}, {6, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
 
 struct Layout {
-    int K = 0;
-    std::vector<int> state_of_pos;              // 32*K, -1 padding
-    std::vector<int> pos_of_state;              // S
-    std::vector<char> chained;                  // per position
-    std::vector<std::vector<Extra>> extras;     // per position, in incoming order
+    int KC = 0, KG = 0, DEG = 2, n_lanes = 0, n_generic = 0;
+    std::vector<int> state_of_pos;   // 32*K, -1 padding
+    std::vector<int> pos_of_state;   // S
 };
 
-int pick_k(int n_pos) {
-    for (int k : kAllowedK)
-        if (32 * k >= n_pos) return k;
-    return -1;
+struct Chains {
+    std::vector<std::vector<int>> seqs;   // maximal chains (>= 1 state each), every state in exactly one
+    std::vector<int> indeg, outdeg;
+};
+
+Chains find_chains(int S, const int32_t *in_ptr, const int32_t *in_idx) {
+    Chains c;
+    c.indeg.assign(S, 0);
+    c.outdeg.assign(S, 0);
+    for (int j = 0; j < S; ++j) {
+        c.indeg[j] = in_ptr[j + 1] - in_ptr[j];
+        for (int e = in_ptr[j]; e < in_ptr[j + 1]; ++e) c.outdeg[in_idx[e]]++;
+    }
+    std::vector<int> link_next(S, -1), link_prev(S, -1);
+    for (int t = 0; t < S; ++t) {
+        if (c.indeg[t] != 1) continue;
+        const int j = in_idx[in_ptr[t]];
+        if (j == t || c.outdeg[j] != 1) continue;
+        link_next[j] = t;
+        link_prev[t] = j;
+    }
+    std::vector<char> seen(S, 0);
+    for (int h = 0; h < S; ++h) {
+        if (link_prev[h] != -1) continue;
+        std::vector<int> seq;
+        for (int j = h; j != -1 && !seen[j]; j = link_next[j]) {
+            seen[j] = 1;
+            seq.push_back(j);
+        }
+        c.seqs.push_back(seq);
+    }
+    for (int h = 0; h < S; ++h)   // pure cycles of links (unreachable in practice)
+        if (!seen[h]) {
+            std::vector<int> seq;
+            for (int j = h; !seen[j]; j = link_next[j]) {
+                seen[j] = 1;
+                seq.push_back(j);
+            }
+            // break the cycle: its first state is treated as a head with a (published) predecessor
+            c.seqs.push_back(seq);
+        }
+    return c;
 }
 
-bool build_layout(int S, const int32_t *in_ptr, const int32_t *in_idx, Layout &L) {
-    // greedy path cover: state j extends the path ending in its closest unextended predecessor
-    std::vector<int> next_in_path(S, -1), prev_in_path(S, -1);
-    for (int j = 0; j < S; ++j) {
-        int best = -1;
-        for (int e = in_ptr[j]; e < in_ptr[j + 1]; ++e) {
-            int p = in_idx[e];
-            if (p < j && next_in_path[p] == -1 && p > best) best = p;
+// lanes each chain gets under a given KC; returns total lanes
+int plan_lanes(const Chains &c, int KC, std::vector<int> &lanes) {
+    lanes.assign(c.seqs.size(), 0);
+    int total = 0;
+    for (size_t i = 0; i < c.seqs.size(); ++i) {
+        const std::vector<int> &q = c.seqs[i];
+        int eligible = (int)q.size();
+        if (c.indeg[q[0]] > 1) eligible -= 1;           // a merge point can only be generic
+        if (c.indeg[q[0]] == 1 && (int)q.size() > 0) {
+            // head with one predecessor: fine as slot 0 as long as that predecessor is published,
+            // which holds because the predecessor ends its own chain (it is not linked to us)
         }
-        if (best >= 0) {
-            next_in_path[best] = j;
-            prev_in_path[j] = best;
+        lanes[i] = eligible / KC;
+        total += lanes[i];
+    }
+    while (total > 32) {   // give lanes back, shortest surplus first: take from the longest chain
+        size_t best = 0;
+        for (size_t i = 1; i < lanes.size(); ++i)
+            if (lanes[i] > lanes[best]) best = i;
+        lanes[best]--;
+        total--;
+    }
+    return total;
+}
+
+int build_layout(int S, const int32_t *in_ptr, const int32_t *in_idx, int mv, Layout &L) {
+    const Chains c = find_chains(S, in_ptr, in_idx);
+    int best_cost = 1 << 30, best_split = -1;
+    std::vector<int> lanes, best_lanes;
+    int max_indeg_all = 0;
+    for (int j = 0; j < S; ++j) max_indeg_all = std::max(max_indeg_all, c.indeg[j]);
+    for (size_t si = 0; si < sizeof(kSplits) / sizeof(kSplits[0]); ++si) {
+        const Split &sp = kSplits[si];
+        if (!((sp.mv_mask >> mv) & 1u)) continue;
+        const int total = plan_lanes(c, sp.kc, lanes);
+        const int generic = S - total * sp.kc;
+        if (generic > 32 * sp.kg) continue;
+        const int deg = max_indeg_all <= 2 ? 2 : 4;
+        const int cost = sp.kc * 9 + sp.kg * (8 + 8 * deg);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_split = (int)si;
+            best_lanes = lanes;
         }
     }
-    std::vector<int> seq;
-    seq.reserve(S);
-    for (int h = 0; h < S; ++h) {
-        if (prev_in_path[h] != -1) continue;
-        for (int j = h; j != -1; j = next_in_path[j]) seq.push_back(j);
+    if (best_split < 0) {
+        bool any_mv = false;
+        for (const Split &sp : kSplits) any_mv |= ((sp.mv_mask >> mv) & 1u) != 0;
+        return any_mv ? WSTR_ERR_TOO_MANY_STATES : WSTR_ERR_UNSUPPORTED;
     }
-    if ((int)seq.size() != S) return false;
-    L.K = pick_k(S);
-    if (L.K < 0) return false;
-    const int NP = 32 * L.K;
+    L.KC = kSplits[best_split].kc;
+    L.KG = kSplits[best_split].kg;
+    const int K = L.KC + L.KG, NP = 32 * K;
     L.state_of_pos.assign(NP, -1);
     L.pos_of_state.assign(S, -1);
-    L.chained.assign(NP, 0);
-    L.extras.assign(NP, {});
-    for (int p = 0; p < S; ++p) {
-        L.state_of_pos[p] = seq[p];
-        L.pos_of_state[seq[p]] = p;
-    }
-    for (int p = 0; p < S; ++p) {
-        const int j = seq[p];
-        const int chain_src = (p > 0 && prev_in_path[j] == seq[p - 1]) ? seq[p - 1] : -1;
-        int chain_rank = -1;
-        if (chain_src >= 0) {
-            for (int e = in_ptr[j]; e < in_ptr[j + 1]; ++e)
-                if (in_idx[e] == chain_src) {
-                    chain_rank = e - in_ptr[j];
-                    break;
-                }
+    int lane = 0;
+    std::vector<int> generic;
+    for (size_t i = 0; i < c.seqs.size(); ++i) {
+        const std::vector<int> &q = c.seqs[i];
+        const int in_lanes = best_lanes[i] * L.KC;
+        const int head = (int)q.size() - in_lanes;
+        for (int n = 0; n < head; ++n) generic.push_back(q[n]);
+        for (int n = head; n < (int)q.size(); ++n) {
+            const int off = n - head;
+            const int pos = (lane + off / L.KC) * K + off % L.KC;
+            L.state_of_pos[pos] = q[n];
+            L.pos_of_state[q[n]] = pos;
         }
-        L.chained[p] = chain_rank >= 0;
-        for (int e = in_ptr[j]; e < in_ptr[j + 1]; ++e) {
-            const int rank = e - in_ptr[j];
-            if (rank == chain_rank) continue;
-            L.extras[p].push_back({in_idx[e], chain_rank >= 0 && rank < chain_rank});
-        }
+        lane += best_lanes[i];
     }
-    return true;
+    L.n_lanes = lane;
+    std::sort(generic.begin(), generic.end());
+    int max_indeg = 0;
+    for (size_t gi = 0; gi < generic.size(); ++gi) {
+        const int g = (int)gi / 32, ln = (int)gi % 32;
+        const int pos = ln * K + L.KC + g;
+        L.state_of_pos[pos] = generic[gi];
+        L.pos_of_state[generic[gi]] = pos;
+        max_indeg = std::max(max_indeg, c.indeg[generic[gi]]);
+    }
+    L.n_generic = (int)generic.size();
+    if (max_indeg > WSTR_MAX_DEG) return WSTR_ERR_UNSUPPORTED;
+    L.DEG = max_indeg <= 2 ? 2 : 4;
+    return WSTR_OK;
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -139,57 +209,73 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
         if (in_idx[e] < 0 || in_idx[e] >= S) return WSTR_ERR_INVALID_ARGUMENT;
 
     Layout L;
-    if (!build_layout(S, in_ptr, in_idx, L)) return WSTR_ERR_TOO_MANY_STATES;
-    const int K = L.K, NP = 32 * K;
+    const int lrc = build_layout(S, in_ptr, in_idx, mv, L);
+    if (lrc != WSTR_OK) return lrc;
+    const int KC = L.KC, KG = L.KG, K = KC + KG, NP = 32 * K;
+    const int inf_cell = KG * 32 + 32;
 
-    // per-slot rows of extra edges
-    std::vector<int> rows_of_slot(K, 0);
-    int n_extra = 0;
-    for (int p = 0; p < NP; ++p) {
-        const int k = p % K;
-        rows_of_slot[k] = std::max(rows_of_slot[k], (int)L.extras[p].size());
-        n_extra += (int)L.extras[p].size();
-        if (L.extras[p].size() > 14) return WSTR_ERR_UNSUPPORTED;   // 4-bit direction codes
-    }
-    DevAutomaton d;
-    memset(&d, 0, sizeof(d));
-    int n_xrows = 0;
-    for (int k = 0; k < K; ++k) {
-        d.xoff[k] = (uint8_t)n_xrows;
-        n_xrows += rows_of_slot[k];
-    }
-    for (int k = K; k <= WSTR_MAX_K; ++k) d.xoff[k] = (uint8_t)n_xrows;
-    if (n_xrows > WSTR_XTAB_MAX_ROWS) return WSTR_ERR_UNSUPPORTED;
+    // published-row index of every state (-1 = not readable by other lanes)
+    auto published = [&](int state) {
+        const int pos = L.pos_of_state[state];
+        const int lane = pos / K, u = pos % K;
+        if (u >= KC) return (u - KC) * 32 + lane;
+        if (u == KC - 1) return KG * 32 + lane;
+        return -1;
+    };
 
-    std::vector<uint16_t> xtab((size_t)std::max(n_xrows, 1) * 32, WSTR_NO_EDGE);
-    std::vector<uint32_t> lane_bits(32 * 4, 0u);
+    std::vector<uint32_t> lane_tab(32 * WSTR_LANE_TAB_STRIDE, 0u);
+    std::vector<int16_t> pred_tab((size_t)NP * WSTR_PRED_STRIDE, (int16_t)-1);
     std::vector<double> v_pos(NP, 0.0);
     std::vector<int16_t> sop(NP, -1);
     const int boundary = flank_length - 10;
     const int after = seq_idx[S - 1] - boundary;     // caller.py:211-212
-    uint32_t extra_slots = 0, src_slots = 0, broken = 0;
-    for (int p = 0; p < NP; ++p) {
-        const int lane = p / K, k = p % K;
-        const int j = L.state_of_pos[p];
-        sop[p] = (int16_t)j;
+    for (int lane = 0; lane < 32; ++lane) {
+        lane_tab[lane * WSTR_LANE_TAB_STRIDE + 1] = (uint32_t)inf_cell;
+        for (int g = 0; g < WSTR_LANE_TAB_STRIDE - 2; ++g)
+            lane_tab[lane * WSTR_LANE_TAB_STRIDE + 2 + g] = (uint32_t)inf_cell * 0x01010101u;
+    }
+    for (int pos = 0; pos < NP; ++pos) {
+        const int lane = pos / K, u = pos % K;
+        const int j = L.state_of_pos[pos];
+        sop[pos] = (int16_t)j;
         if (j < 0) continue;
-        v_pos[p] = values[j];
-        lane_bits[96 + lane] |= 1u << k;
-        if (L.chained[p]) lane_bits[lane] |= 1u << k;
-        else broken |= 1u << k;
-        if (seq_idx[j] < after) lane_bits[32 + lane] |= 1u << k;
-        for (size_t r = 0; r < L.extras[p].size(); ++r) {
-            const int sp = L.pos_of_state[L.extras[p][r].src_state];
-            xtab[(size_t)(d.xoff[k] + r) * 32 + lane] = (uint16_t)(sp | (L.extras[p][r].before_chain ? 0x8000 : 0));
-            lane_bits[64 + sp / K] |= 1u << (sp % K);
-            src_slots |= 1u << (sp % K);
-            extra_slots |= 1u << k;
+        v_pos[pos] = values[j];
+        if (seq_idx[j] < after) lane_tab[lane * WSTR_LANE_TAB_STRIDE + 0] |= 1u << u;
+        const int deg = in_ptr[j + 1] - in_ptr[j];
+        if (u < KC) {
+            if (deg > 1) return WSTR_ERR_UNSUPPORTED;          // cannot happen: layout invariant
+            if (deg == 1) {
+                const int pstate = in_idx[in_ptr[j]];
+                const int ppos = L.pos_of_state[pstate];
+                pred_tab[(size_t)pos * WSTR_PRED_STRIDE + 1] = (int16_t)ppos;
+                if (u == 0) {
+                    const int q = published(pstate);
+                    if (q < 0) return WSTR_ERR_UNSUPPORTED;    // layout invariant
+                    lane_tab[lane * WSTR_LANE_TAB_STRIDE + 1] = (uint32_t)q;
+                } else if (ppos != pos - 1) {
+                    return WSTR_ERR_UNSUPPORTED;               // layout invariant
+                }
+            } else if (u != 0) {
+                return WSTR_ERR_UNSUPPORTED;                   // a source state can only open a lane
+            }
+        } else {
+            uint32_t packed = 0;
+            for (int r = 0; r < WSTR_MAX_DEG; ++r) {
+                int q = inf_cell;
+                if (r < deg) {
+                    const int pstate = in_idx[in_ptr[j] + r];
+                    q = published(pstate);
+                    if (q < 0) return WSTR_ERR_UNSUPPORTED;    // layout invariant
+                    pred_tab[(size_t)pos * WSTR_PRED_STRIDE + 1 + r] = (int16_t)L.pos_of_state[pstate];
+                }
+                packed |= (uint32_t)q << (8 * r);
+            }
+            lane_tab[lane * WSTR_LANE_TAB_STRIDE + 2 + (u - KC)] = packed;
         }
     }
-    // padding positions never hold a finite cost; their chain bit stays 0
-    for (int p = 0; p < NP; ++p)
-        if (L.state_of_pos[p] < 0) broken |= 1u << (p % K);
 
+    DevAutomaton d;
+    memset(&d, 0, sizeof(d));
     // one device blob
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -198,13 +284,13 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
         return o;
     };
     const size_t o_v = take(sizeof(double) * NP), o_sop = take(sizeof(int16_t) * NP),
-                 o_bits = take(sizeof(uint32_t) * 128), o_x = take(sizeof(uint16_t) * xtab.size()),
+                 o_lt = take(sizeof(uint32_t) * lane_tab.size()), o_pt = take(sizeof(int16_t) * pred_tab.size()),
                  o_val = take(sizeof(double) * S), o_sq = take(sizeof(int32_t) * S), o_rm = take(S), o_lb = take(S);
     std::vector<unsigned char> blob(off, 0);
     memcpy(blob.data() + o_v, v_pos.data(), sizeof(double) * NP);
     memcpy(blob.data() + o_sop, sop.data(), sizeof(int16_t) * NP);
-    memcpy(blob.data() + o_bits, lane_bits.data(), sizeof(uint32_t) * 128);
-    memcpy(blob.data() + o_x, xtab.data(), sizeof(uint16_t) * xtab.size());
+    memcpy(blob.data() + o_lt, lane_tab.data(), sizeof(uint32_t) * lane_tab.size());
+    memcpy(blob.data() + o_pt, pred_tab.data(), sizeof(int16_t) * pred_tab.size());
     memcpy(blob.data() + o_val, values, sizeof(double) * S);
     memcpy(blob.data() + o_sq, seq_idx, sizeof(int32_t) * S);
     if (rep_mask) memcpy(blob.data() + o_rm, rep_mask, S);
@@ -220,28 +306,26 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     unsigned char *base = static_cast<unsigned char *>(d_blob);
     d.v_pos = reinterpret_cast<const double *>(base + o_v);
     d.state_of_pos = reinterpret_cast<const int16_t *>(base + o_sop);
-    d.lane_bits = reinterpret_cast<const uint32_t *>(base + o_bits);
-    d.xtab = reinterpret_cast<const uint16_t *>(base + o_x);
+    d.lane_tab = reinterpret_cast<const uint32_t *>(base + o_lt);
+    d.pred_tab = reinterpret_cast<const int16_t *>(base + o_pt);
     d.K = K;
+    d.KC = KC;
+    d.KG = KG;
+    d.DEG = L.DEG;
     d.W = (K + 7) / 8;
     d.S = S;
-    d.n_xrows = n_xrows;
     d.end_pos = L.pos_of_state[endstate];
     d.mv = mv;
     d.th1 = 6 * boundary;
     d.band6 = 6 * boundary;
     for (int c = 0; c <= mv; ++c) d.init_pos[c] = L.pos_of_state[c];
-    d.allchain_slots = ~broken;
-    d.extra_slots = extra_slots;
-    d.src_slots = src_slots;
 
     wstr_automaton *a = new wstr_automaton();
     a->dev = d;
     a->d_blob = d_blob;
     a->n_edges = E;
-    a->n_extra = n_extra;
-    a->n_extra_slots = __builtin_popcount(extra_slots);
-    a->n_broken_slots = __builtin_popcount(broken & ((1u << K) - 1));
+    a->n_generic = L.n_generic;
+    a->n_chain_lanes = L.n_lanes;
     a->flank_length = flank_length;
     a->h_state_of_pos = new int32_t[NP];
     for (int p = 0; p < NP; ++p) a->h_state_of_pos[p] = L.state_of_pos[p];
@@ -250,6 +334,24 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     a->d_rep_mask = base + o_rm;
     a->d_last_base = base + o_lb;
     *out = a;
+    return WSTR_OK;
+}
+
+extern "C" int wstr_automaton_plan(const int32_t *in_ptr, const int32_t *in_idx, int32_t S, int32_t mv,
+                                   int32_t *info, int32_t *state_of_pos, int32_t n_pos) {
+    if (!in_ptr || !info || S <= 0) return WSTR_ERR_INVALID_ARGUMENT;
+    if (mv < 2 || mv > WSTR_MAX_MV) return WSTR_ERR_UNSUPPORTED;
+    if (S > 32 * WSTR_MAX_K) return WSTR_ERR_TOO_MANY_STATES;
+    Layout L;
+    const int rc = build_layout(S, in_ptr, in_idx, mv, L);
+    if (rc != WSTR_OK) return rc;
+    info[0] = L.KC;
+    info[1] = L.KG;
+    info[2] = L.DEG;
+    info[3] = L.n_lanes;
+    info[4] = L.n_generic;
+    if (state_of_pos)
+        for (int p = 0; p < n_pos && p < 32 * (L.KC + L.KG); ++p) state_of_pos[p] = L.state_of_pos[p];
     return WSTR_OK;
 }
 
@@ -263,8 +365,7 @@ extern "C" int wstr_automaton_destroy(wstr_automaton *a) {
 
 extern "C" int wstr_automaton_info(const wstr_automaton *a, int32_t *info, int32_t n_info) {
     if (!a || !info) return WSTR_ERR_INVALID_ARGUMENT;
-    const int32_t vals[7] = {a->dev.K, a->dev.W, a->n_extra, a->n_extra_slots, a->dev.S, a->n_edges,
-                             a->n_broken_slots};
+    const int32_t vals[7] = {a->dev.K, a->dev.W, a->dev.KC, a->dev.KG, a->dev.S, a->n_edges, a->n_generic};
     for (int i = 0; i < n_info && i < 7; ++i) info[i] = vals[i];
     return WSTR_OK;
 }
@@ -384,15 +485,22 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
         WSTR_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(ReadMeta) * nw, cudaMemcpyHostToDevice, s));
         WSTR_CUDA(cudaMemsetAsync(d_queue, 0, 64 * sizeof(int32_t), s));
 
-        // one launch per kernel width present in this wave
+        // one launch per kernel shape (chain slots, generic slots, in-degree) present in this wave
         order.assign(nw, 0);
         int filled = 0, cls = 0;
-        for (int k : kAllowedK) {
+        std::vector<char> done(nw, 0);
+        for (int i0 = 0; i0 < nw; ++i0) {
+            if (done[i0]) continue;
+            const DevAutomaton &ref = automata[meta[i0].aut]->dev;
             const int begin = filled;
-            for (int i = 0; i < nw; ++i)
-                if (automata[meta[i].aut]->dev.K == k) order[filled++] = i;
-            if (filled == begin) continue;
-            // within a width: by automaton among equal lengths is already implied by the stable sort
+            for (int i = i0; i < nw; ++i) {
+                const DevAutomaton &o = automata[meta[i].aut]->dev;
+                if (!done[i] && o.KC == ref.KC && o.KG == ref.KG && o.DEG == ref.DEG) {
+                    order[filled++] = i;
+                    done[i] = 1;
+                }
+            }
+            if (cls >= 64) return WSTR_ERR_UNSUPPORTED;
             WSTR_CUDA(cudaMemcpyAsync(d_order + begin, order.data() + begin, sizeof(int32_t) * (filled - begin),
                                       cudaMemcpyHostToDevice, s));
             FillParams fp;
@@ -406,7 +514,7 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
             fp.dir = d_dir;
             fp.end_cost = d_end_cost;
             fp.status = d_status;
-            int rc = wstr_launch_fill(k, mv, fp, s);
+            int rc = wstr_launch_fill(ref.KC, ref.KG, ref.DEG, mv, fp, s);
             if (rc != WSTR_OK) return rc;
             ++cls;
         }

@@ -3,24 +3,29 @@
 // Replaces WarpSTR._calc_dtw_astates (reference src/caller/caller.py:198-245) and
 // WarpSTR._backtracking (:247-301).
 //
-// One warp owns one read.  The automaton's states live in registers, K consecutive
-// positions per lane (position p = lane*K + slot); a position is "chained" when the edge
-// (p-1 -> p) exists, which the host-side layout arranges for almost every state.  Row i
-// of the DP needs only row i-1 (stay) and row i-back (skip through an incoming state), so
-// per position the warp carries D[i-1] and the running partial sums
+// One warp owns one read; the automaton's states live in registers, K = KC + KG per lane:
+//   * KC "chain" slots: lane l holds KC consecutive states of a pure chain (every state has
+//     exactly one incoming edge, from the state before it: the flanks).  Its skip candidate
+//     comes from the neighbouring register; slot 0 reads the previous lane's tail.
+//   * KG "generic" slots: one arbitrary state per lane and slot (the repeat region: loop
+//     back-edges, optional-group skips, IUPAC fan-in, context copies).  Up to DEG incoming
+//     edges each, kept in the reference's incoming order, gathered from a small published
+//     row in shared memory.
+// Row i of the DP needs only row i-1 (stay) and row i-back (skip through an incoming state),
+// so per state the warp carries D[i-1] and the running partial sums
 //     P_m[t] = D[t] + |x[t+1]-v| + ... + |x[t+m]-v|        m = 1..mv-1
-// in the reference's own left-to-right addition order; the skip candidate into state j
-// over incoming state p is P_{back-1}[i-back][p] + |x[i]-v_j|, bit-identical to the
-// reference's nested loop.  Chained candidates come from the neighbouring register (one
-// 64-bit shuffle per row at the lane boundary), the few remaining edges (loop back-edges,
-// optional-group skips, IUPAC fan-in) through a double-buffered shared-memory row.
-// All arithmetic is FP64 add/abs/compare: no multiply, so no FMA contraction can occur.
+// in the reference's own left-to-right addition order; the skip candidate into state j over
+// incoming state p is P_{back-1}[i-back][p] + |x[i]-v_j|, bit-identical to the reference's
+// nested loop.  Every row each lane publishes the values other lanes may need (its generic
+// states and its chain tail, KG+1 stores), one __syncwarp, then everything is branch-free:
+// lanes with fewer edges read a cell that always holds +inf.  All arithmetic is FP64
+// add/abs/compare: no multiply, so no FMA contraction can occur.
 //
-// The read's signal is streamed through shared memory in 2 KB tiles with 1-D bulk async
+// The read's signal is streamed through shared memory in 1 KB tiles with 1-D bulk async
 // copies (cp.async.bulk + mbarrier, TMA engine) two tiles ahead of the row loop.
-// Output: one 4-bit direction code per cell (0 stay, 1 chain, 2+r = r-th extra edge of
-// the position), packed 8 per 32-bit word, stored row-major [row][word][lane] so that every
-// row is one coalesced 128-byte line per word.  D itself never leaves the SM.
+// Output: one 4-bit direction code per cell (0 stay, c>0 = c-th incoming edge), packed 8 per
+// 32-bit word, stored row-major [row][word][lane] so that every row is one coalesced
+// 128-byte line per word.  D itself never leaves the SM.
 #include "wstr_internal.h"
 
 namespace {
@@ -71,7 +76,7 @@ struct LaneState {
     double P[MV - 1][K];   // P[m-1] = P_m
 };
 
-// the pipeline value a position offers to its successors in this row
+// the pipeline value a state offers to its successors in this row
 template <int K, int MV, bool SHORT>
 __device__ __forceinline__ double offer(const LaneState<K, MV> &s, int k) {
     if (SHORT) {
@@ -81,69 +86,50 @@ __device__ __forceinline__ double offer(const LaneState<K, MV> &s, int k) {
     return s.P[MV - 2][k];
 }
 
-struct LaneTables {
-    uint32_t chain_bits, band_bits, src_bits;       // per lane, K bits each
-    uint32_t allchain_slots, extra_slots, src_slots;  // warp-uniform
+template <int KG>
+struct LaneConsts {
+    uint32_t band_bits;     // slot u of this lane is inside the end band's skipped prefix
+    uint32_t src0;          // byte offset (within a published row) of chain slot 0's predecessor
+    uint32_t gsrc[KG];      // generic slot g: 4 x 8-bit published-row indices, incoming order
 };
+
+// published row: [generic g][lane] ... [chain tail][lane], [+inf cell]
+template <int KG>
+__host__ __device__ constexpr int q_row_len() { return 32 * KG + 40; }
 
 // One DP row.  SHORT: this row allows dwell mv-1 (masked row of the second pass).
 // BAND: the end band is active (caller.py:223-224).
-template <int K, int MV, bool SHORT, bool BAND>
-__device__ __forceinline__ void dp_row(LaneState<K, MV> &s, const LaneTables &lt, const double x,
-                                       double *__restrict__ Qs, const uint16_t *__restrict__ xtab,
-                                       const uint8_t *__restrict__ xoff, const int lane,
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
+__device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc, const double x,
+                                       double *__restrict__ Q, const int lane,
                                        uint32_t *__restrict__ dir_row) {
+    constexpr int K = KC + KG;
     constexpr int W = (K + 7) / 8;
     const double INF = dinf();
 
-    if (lt.src_slots) {   // publish the values that non-chained edges read
+    // what other lanes may read this row: my generic states and my chain tail
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if ((lt.src_slots >> k) & 1u) {
-                if ((lt.src_bits >> k) & 1u) Qs[lane * K + k] = offer<K, MV, SHORT>(s, k);
-            }
-        }
-        __syncwarp();
-    }
-    double qprev = __shfl_up_sync(FULL, offer<K, MV, SHORT>(s, K - 1), 1);
+    for (int g = 0; g < KG; ++g) Q[g * 32 + lane] = offer<K, MV, SHORT>(s, KC + g);
+    Q[KG * 32 + lane] = offer<K, MV, SHORT>(s, KC - 1);
+    __syncwarp();
 
     uint32_t codes[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) codes[w] = 0u;
 
+    // ---- chain slots: stay or the single incoming edge -----------------------------------
+    double qprev = *reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(Q) + lc.src0);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < KC; ++k) {
         const double ae = fabs(x - s.v[k]);
         const double qhere = offer<K, MV, SHORT>(s, k);
         const double stay = s.D[k] + ae;
-        double ch = qprev + ae;
-        if (!((lt.allchain_slots >> k) & 1u)) {
-            if (!((lt.chain_bits >> k) & 1u)) ch = INF;
-        }
-        double best = stay;
-        uint32_t code = 0u;
-        if (ch < best) {
-            best = ch;
-            code = 1u;
-        }
-        if ((lt.extra_slots >> k) & 1u) {
-            const int r0 = xoff[k], r1 = xoff[k + 1];
-            for (int r = r0; r < r1; ++r) {
-                const uint32_t ent = xtab[r * 32 + lane];
-                if (ent != WSTR_NO_EDGE) {
-                    const double c = Qs[ent & 0x7fffu] + ae;
-                    // an edge listed before the chain edge in the reference's incoming order
-                    // beats it on ties; everything else needs a strictly smaller cost
-                    const bool tie = (ent >> 15) && code == 1u && c == best;
-                    if (c < best || tie) {
-                        best = c;
-                        code = 2u + static_cast<uint32_t>(r - r0);
-                    }
-                }
-            }
-        }
+        const double ch = qprev + ae;
+        const bool take = ch < stay;
+        double best = take ? ch : stay;
+        uint32_t code = take ? 1u : 0u;
         if (BAND) {
-            if ((lt.band_bits >> k) & 1u) {
+            if ((lc.band_bits >> k) & 1u) {
                 best = INF;
                 code = 0u;
             }
@@ -155,29 +141,56 @@ __device__ __forceinline__ void dp_row(LaneState<K, MV> &s, const LaneTables &lt
         qprev = qhere;
         codes[k >> 3] |= code << (4 * (k & 7));
     }
+
+    // ---- generic slots: stay, then up to DEG incoming edges in list order --------------------
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+        const int k = KC + g;
+        const double ae = fabs(x - s.v[k]);
+        const double stay = s.D[k] + ae;
+        double best = stay;
+        uint32_t code = 0u;
+#pragma unroll
+        for (int r = 0; r < DEG; ++r) {
+            const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
+            const double c = Q[idx] + ae;
+            if (c < best) {
+                best = c;
+                code = static_cast<uint32_t>(r + 1);
+            }
+        }
+        if (BAND) {
+            if ((lc.band_bits >> k) & 1u) {
+                best = INF;
+                code = 0u;
+            }
+        }
+#pragma unroll
+        for (int m = MV - 2; m >= 1; --m) s.P[m][k] = s.P[m - 1][k] + ae;
+        s.P[0][k] = stay;
+        s.D[k] = best;
+        codes[k >> 3] |= code << (4 * (k & 7));
+    }
 #pragma unroll
     for (int w = 0; w < W; ++w) dir_row[w * 32 + lane] = codes[w];
 }
 
-template <int K>
-struct FillSmem {
+// per-warp shared memory: [sig 2 x CH f64][published rows 2 x q_row_len f64][2 mbarriers]
+template <int KG>
+struct alignas(16) FillSmem {
     double sig[2][CH];
-    double Qs[2][32 * K];
-    uint16_t xtab[WSTR_XTAB_MAX_ROWS * 32];
+    double Q[2][q_row_len<KG>()];
     uint64_t bar[2];
-    uint8_t xoff[32];
 };
 
-template <int K>
-constexpr int fill_min_blocks() { return K <= 8 ? 4 : (K <= 12 ? 3 : 2); }
-
-template <int K, int MV>
-__global__ void __launch_bounds__(32 * WSTR_WARPS_PER_CTA, fill_min_blocks<K>())
+template <int KC, int KG, int DEG, int MV>
+__global__ void __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 8 ? 4 : (KC + KG <= 12 ? 3 : 2)))
 dtw_fill_kernel(const FillParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int K = KC + KG;
     constexpr int W = (K + 7) / 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FillSmem<K> &sm = reinterpret_cast<FillSmem<K> *>(smem_raw)[warp];
+    FillSmem<KG> &sm = reinterpret_cast<FillSmem<KG> *>(smem_raw)[warp];
     const double INF = dinf();
 
     if (lane == 0) {
@@ -185,11 +198,12 @@ dtw_fill_kernel(const FillParams p) {
         mbar_init(&sm.bar[1], 1);
         fence_barrier_init();
     }
+    for (int e = lane; e < 2 * q_row_len<KG>(); e += 32) (&sm.Q[0][0])[e] = INF;   // incl. the +inf cell
     __syncwarp();
     uint32_t uses0 = 0, uses1 = 0;   // completed phases of the two tile barriers
 
     LaneState<K, MV> s;
-    LaneTables lt;
+    LaneConsts<KG> lc;
     int cached_aut = -1;
     double v0 = 0.0;
 
@@ -206,22 +220,15 @@ dtw_fill_kernel(const FillParams p) {
             continue;
         }
 
-        if (m.aut != cached_aut) {   // (re)load the automaton into registers / shared memory
-            __syncwarp();
+        if (m.aut != cached_aut) {   // (re)load the automaton into registers
 #pragma unroll
             for (int k = 0; k < K; ++k) s.v[k] = __ldg(A->v_pos + lane * K + k);
-            lt.chain_bits = __ldg(A->lane_bits + lane);
-            lt.band_bits = __ldg(A->lane_bits + 32 + lane);
-            lt.src_bits = __ldg(A->lane_bits + 64 + lane);
-            lt.allchain_slots = A->allchain_slots;
-            lt.extra_slots = A->extra_slots;
-            lt.src_slots = A->src_slots;
-            const int nx = A->n_xrows * 32;
-            for (int e = lane; e < nx; e += 32) sm.xtab[e] = __ldg(A->xtab + e);
-            if (lane <= K) sm.xoff[lane] = A->xoff[lane];
+            lc.band_bits = __ldg(A->lane_tab + lane * WSTR_LANE_TAB_STRIDE + 0);
+            lc.src0 = __ldg(A->lane_tab + lane * WSTR_LANE_TAB_STRIDE + 1) * 8u;
+#pragma unroll
+            for (int g = 0; g < KG; ++g) lc.gsrc[g] = __ldg(A->lane_tab + lane * WSTR_LANE_TAB_STRIDE + 2 + g);
             v0 = __ldg(A->v_pos + A->init_pos[0]);
             cached_aut = m.aut;
-            __syncwarp();
         }
 
         // ---- signal tiles: two in flight --------------------------------------------------
@@ -232,8 +239,8 @@ dtw_fill_kernel(const FillParams p) {
                 int n = T - c * CH;
                 n = n > CH ? CH : n;
                 n = (n + 1) & ~1;   // 16-byte granules
-                bulk_load(sm.sig[c & 1], gsig + static_cast<int64_t>(c) * CH,
-                          static_cast<uint32_t>(n) * 8u, &sm.bar[c & 1]);
+                bulk_load(sm.sig[c & 1], gsig + static_cast<int64_t>(c) * CH, static_cast<uint32_t>(n) * 8u,
+                          &sm.bar[c & 1]);
             }
         };
         issue(0);
@@ -301,18 +308,18 @@ dtw_fill_kernel(const FillParams p) {
                 }
                 const double x = xs[i & (CH - 1)];
                 const bool shortrow = (mw >> (i & 31)) & 1u;
-                double *Qs = sm.Qs[i & 1];
+                double *Q = sm.Q[i & 1];
                 uint32_t *dir_row = dir + static_cast<int64_t>(i) * (W * 32);
                 if (i < band_start) {
                     if (shortrow)
-                        dp_row<K, MV, true, false>(s, lt, x, Qs, sm.xtab, sm.xoff, lane, dir_row);
+                        dp_row<KC, KG, DEG, MV, true, false>(s, lc, x, Q, lane, dir_row);
                     else
-                        dp_row<K, MV, false, false>(s, lt, x, Qs, sm.xtab, sm.xoff, lane, dir_row);
+                        dp_row<KC, KG, DEG, MV, false, false>(s, lc, x, Q, lane, dir_row);
                 } else {
                     if (shortrow)
-                        dp_row<K, MV, true, true>(s, lt, x, Qs, sm.xtab, sm.xoff, lane, dir_row);
+                        dp_row<KC, KG, DEG, MV, true, true>(s, lc, x, Q, lane, dir_row);
                     else
-                        dp_row<K, MV, false, true>(s, lt, x, Qs, sm.xtab, sm.xoff, lane, dir_row);
+                        dp_row<KC, KG, DEG, MV, false, true>(s, lc, x, Q, lane, dir_row);
                 }
             }
             __syncwarp();                          // every lane is done with this tile
@@ -344,6 +351,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TraceParams p) {
     const DevAutomaton *A = p.auts + m.aut;
     const int K = A->K, W = A->W, mv = A->mv;
     const int16_t *sop = A->state_of_pos;
+    const int16_t *pred = A->pred_tab;
     const uint32_t *dir = p.dir + m.dir_off;
     const uint32_t *mw = p.maskbits ? p.maskbits + m.mask_off : nullptr;
     int32_t *tr = p.trace + m.sig_off;
@@ -365,12 +373,11 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TraceParams p) {
         }
         int back = mv;
         if (mw && ((mw[i >> 5] >> (i & 31)) & 1u)) back = mv - 1;
-        if (i < back) {
+        const int ppos = pred[pos * WSTR_PRED_STRIDE + static_cast<int>(code)];
+        if (i < back || ppos < 0) {
             p.status[m.read] = WSTR_READ_BACKTRACK;
             return;
         }
-        const int ppos = code == 1u ? pos - 1
-                                    : (A->xtab[(A->xoff[k] + static_cast<int>(code) - 2) * 32 + lane] & 0x7fff);
         const int pst = sop[ppos];
         for (int r = 1; r < back; ++r) tr[i - r] = pst;
         i -= back;
@@ -380,16 +387,17 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TraceParams p) {
     tr[0] = st;
 }
 
-template <int K, int MV>
+template <int KC, int KG, int DEG, int MV>
 int launch_fill_t(const FillParams &p, cudaStream_t s) {
     static int grid_cap = 0;
-    const int smem = static_cast<int>(sizeof(FillSmem<K>)) * WSTR_WARPS_PER_CTA;
+    const int smem = static_cast<int>(sizeof(FillSmem<KG>)) * WSTR_WARPS_PER_CTA;
     if (grid_cap == 0) {
-        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<K, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0, sms = 0, per_sm = 0;
         WSTR_CUDA(cudaGetDevice(&dev));
         WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        WSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_fill_kernel<K, MV>,
+        WSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_fill_kernel<KC, KG, DEG, MV>,
                                                                 32 * WSTR_WARPS_PER_CTA, smem));
         if (per_sm < 1) per_sm = 1;
         grid_cap = sms * per_sm;
@@ -397,45 +405,34 @@ int launch_fill_t(const FillParams &p, cudaStream_t s) {
     int grid = (p.n + WSTR_WARPS_PER_CTA - 1) / WSTR_WARPS_PER_CTA;
     if (grid > grid_cap) grid = grid_cap;
     if (grid < 1) return WSTR_OK;
-    dtw_fill_kernel<K, MV><<<grid, 32 * WSTR_WARPS_PER_CTA, smem, s>>>(p);
+    dtw_fill_kernel<KC, KG, DEG, MV><<<grid, 32 * WSTR_WARPS_PER_CTA, smem, s>>>(p);
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;
 }
 
-template <int MV>
-int launch_fill_k(int K, const FillParams &p, cudaStream_t s) {
-    switch (K) {
-        case 4: return launch_fill_t<4, MV>(p, s);
-        case 8: return launch_fill_t<8, MV>(p, s);
-        case 9: return launch_fill_t<9, MV>(p, s);
-        case 10: return launch_fill_t<10, MV>(p, s);
-        case 12: return launch_fill_t<12, MV>(p, s);
-        case 16: return launch_fill_t<16, MV>(p, s);
-        default: return WSTR_ERR_TOO_MANY_STATES;
-    }
+template <int KC, int KG, int MV>
+int launch_fill_deg(int deg, const FillParams &p, cudaStream_t s) {
+    if (deg <= 2) return launch_fill_t<KC, KG, 2, MV>(p, s);
+    return launch_fill_t<KC, KG, 4, MV>(p, s);
 }
 
 }  // namespace
 
-int wstr_fill_smem_bytes(int K) {
-    switch (K) {
-        case 4: return sizeof(FillSmem<4>) * WSTR_WARPS_PER_CTA;
-        case 8: return sizeof(FillSmem<8>) * WSTR_WARPS_PER_CTA;
-        case 9: return sizeof(FillSmem<9>) * WSTR_WARPS_PER_CTA;
-        case 10: return sizeof(FillSmem<10>) * WSTR_WARPS_PER_CTA;
-        case 12: return sizeof(FillSmem<12>) * WSTR_WARPS_PER_CTA;
-        case 16: return sizeof(FillSmem<16>) * WSTR_WARPS_PER_CTA;
-        default: return -1;
-    }
-}
-
-int wstr_launch_fill(int K, int mv, const FillParams &p, cudaStream_t s) {
-    switch (mv) {
-        case 4: return launch_fill_k<4>(K, p, s);
-        case 3: return launch_fill_k<3>(K, p, s);
-        case 5: return launch_fill_k<5>(K, p, s);
-        default: return WSTR_ERR_UNSUPPORTED;
-    }
+// the (chain, generic) slot splits the library is built with; keep in sync with kSplits in api.cu
+int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    if (deg > 4) return WSTR_ERR_UNSUPPORTED;
+#define WSTR_CASE(KC_, KG_, MV_) \
+    if (kc == KC_ && kg == KG_ && mv == MV_) return launch_fill_deg<KC_, KG_, MV_>(deg, p, s);
+    WSTR_CASE(6, 2, 4)
+    WSTR_CASE(6, 2, 3)
+    WSTR_CASE(6, 2, 5)
+    WSTR_CASE(4, 4, 4)
+    WSTR_CASE(8, 2, 4)
+    WSTR_CASE(6, 4, 4)
+    WSTR_CASE(8, 4, 4)
+    WSTR_CASE(12, 4, 4)
+#undef WSTR_CASE
+    return WSTR_ERR_UNSUPPORTED;
 }
 
 int wstr_launch_traceback(const TraceParams &p, cudaStream_t s) {

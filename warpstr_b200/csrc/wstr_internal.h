@@ -7,34 +7,29 @@
 
 #define WSTR_MAX_K 16            // states per lane in the widest kernel (32*16 = 512 positions)
 #define WSTR_MAX_MV 8
-#define WSTR_SIG_CHUNK 256       // samples per bulk-copied signal tile (2 KB)
+#define WSTR_SIG_CHUNK 128       // samples per bulk-copied signal tile (1 KB)
 #define WSTR_WARPS_PER_CTA 4
-#define WSTR_XTAB_MAX_ROWS 48    // rows of 32 extra-edge entries kept in shared memory per warp
-#define WSTR_NO_EDGE 0xFFFFu
+#define WSTR_MAX_DEG 4           // incoming edges of a generic-slot state
+#define WSTR_LANE_TAB_STRIDE 8   // u32 per lane: band bits, slot-0 source, gsrc[0..5]
+#define WSTR_PRED_STRIDE 8       // i16 per position: predecessor position by direction code
 
-// Device view of one automaton laid out for the warp-per-read kernel.
-// Position p = lane*K + slot.  A "chain" edge is the edge (p-1 -> p): it is served from
-// registers (same lane) or one shuffle (slot 0).  Every other incoming edge is an "extra":
-// its source publishes its pipeline value to shared memory each row.
+// Device view of one automaton laid out for the warp-per-read kernel (see dtw.cu).
+// Position p = lane*K + u; u < KC is a chain slot, u >= KC the generic slot u-KC.
+// Published-row index of a value other lanes can read: generic (g, lane) -> g*32 + lane,
+// chain tail of lane -> KG*32 + lane, the constant +inf cell -> KG*32 + 32.
 struct DevAutomaton {
     const double *v_pos;             // [32*K] level per position (0 for padding)
     const int16_t *state_of_pos;     // [32*K] state index, -1 = padding
-    const uint32_t *lane_bits;       // [32*4]: chain / band / src / real bits per lane (K bits each)
-    const uint16_t *xtab;            // [n_xrows*32] src_pos | before<<15, WSTR_NO_EDGE = none
-    uint8_t xoff[WSTR_MAX_K + 1];    // rows of slot k are xoff[k] .. xoff[k+1]
-    uint8_t pad_[3];
-    int32_t K;                       // slots per lane
+    const uint32_t *lane_tab;        // [32][WSTR_LANE_TAB_STRIDE]
+    const int16_t *pred_tab;         // [32*K][WSTR_PRED_STRIDE]: predecessor position for code c (-1 none)
+    int32_t K, KC, KG, DEG;
     int32_t W;                       // direction words per lane per row (4 bits per slot)
     int32_t S;                       // states
-    int32_t n_xrows;
     int32_t end_pos;                 // position of the end state
     int32_t mv;                      // min_values_per_state
     int32_t th1;                     // 6*(flank_length-10)
     int32_t band6;                   // 6*(flank_length-10) (second threshold = T - band6)
     int32_t init_pos[WSTR_MAX_MV + 1];  // positions of states 0..mv (row-0 initialisation)
-    uint32_t allchain_slots;         // slot k: every lane's position is chained
-    uint32_t extra_slots;            // slot k has at least one extra edge
-    uint32_t src_slots;              // slot k holds at least one extra-edge source
 };
 
 // Per-read record of one wave.
@@ -74,7 +69,7 @@ struct TraceParams {
 struct wstr_automaton {
     DevAutomaton dev;            // pointers into d_blob
     void *d_blob;
-    int32_t n_edges, n_extra, n_extra_slots, n_broken_slots;
+    int32_t n_edges, n_generic, n_chain_lanes;
     int32_t flank_length;
     int32_t *h_state_of_pos;     // host copy, 32*K
     // tables kept for the mid-stage kernels (device, inside d_blob)
@@ -93,6 +88,5 @@ int wstr_set_cuda_error(cudaError_t e, const char *where);
     } while (0)
 
 // kernels / launchers (dtw.cu)
-int wstr_launch_fill(int K, int mv, const FillParams &p, cudaStream_t s);
+int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
 int wstr_launch_traceback(const TraceParams &p, cudaStream_t s);
-int wstr_fill_smem_bytes(int K);
