@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libwarpstr_b200.so')
+LIB_PATH = os.environ.get('WSTR_LIB') or os.path.join(_HERE, 'libwarpstr_b200.so')
 
 _lib = None
 

@@ -512,22 +512,13 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
             fp.signal = d_signal;
             fp.maskbits = d_maskbits;
             fp.dir = d_dir;
+            fp.trace = d_trace;
             fp.end_cost = d_end_cost;
             fp.status = d_status;
             int rc = wstr_launch_fill(ref.KC, ref.KG, ref.DEG, mv, fp, s);
             if (rc != WSTR_OK) return rc;
             ++cls;
         }
-        TraceParams tp;
-        tp.auts = d_auts;
-        tp.meta = d_meta;
-        tp.n = nw;
-        tp.maskbits = d_maskbits;
-        tp.dir = d_dir;
-        tp.trace = d_trace;
-        tp.status = d_status;
-        int rc = wstr_launch_traceback(tp, s);
-        if (rc != WSTR_OK) return rc;
         if (cursor < (size_t)n_reads) {
             // the next wave overwrites meta/order staging on the host side; the device copies are
             // stream-ordered, but the pageable source vectors are reused, so drain first

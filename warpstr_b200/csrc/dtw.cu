@@ -69,21 +69,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
+// Per-state registers of one lane.  R holds the mv-1 running partial sums; to avoid moving
+// them down the pipeline every row their roles rotate instead: at phase ph the sum P_m lives
+// in R[(m - 1 - ph) mod (mv-1)].  A row adds the emission in place to P_1..P_{mv-2} (which
+// thereby become P_2..P_{mv-1}) and overwrites the register that held P_{mv-1} with the new
+// P_1; mv-1 consecutive rows bring every role back to its register.
 template <int K, int MV>
 struct LaneState {
     double v[K];
     double D[K];
-    double P[MV - 1][K];   // P[m-1] = P_m
+    double R[MV - 1][K];
 };
 
+template <int MV>
+__host__ __device__ constexpr int role_reg(int m, int ph) {   // register of P_m at phase ph
+    return ((m - 1 - ph) % (MV - 1) + (MV - 1)) % (MV - 1);
+}
+
 // the pipeline value a state offers to its successors in this row
-template <int K, int MV, bool SHORT>
+template <int K, int MV, bool SHORT, int PH>
 __device__ __forceinline__ double offer(const LaneState<K, MV> &s, int k) {
     if (SHORT) {
-        if (MV >= 3) return s.P[MV >= 3 ? MV - 3 : 0][k];
+        if (MV >= 3) return s.R[role_reg<MV>(MV >= 3 ? MV - 2 : 1, PH)][k];
         return s.D[k];
     }
-    return s.P[MV - 2][k];
+    return s.R[role_reg<MV>(MV - 1, PH)][k];
+}
+
+// shift the pipeline of state k by one row: P_m += emission for m < mv-1, P_1 = stay
+template <int K, int MV, int PH>
+__device__ __forceinline__ void advance(LaneState<K, MV> &s, int k, double ae, double stay) {
+#pragma unroll
+    for (int m = MV - 2; m >= 1; --m) s.R[role_reg<MV>(m, PH)][k] += ae;
+    s.R[role_reg<MV>(MV - 1, PH)][k] = stay;
 }
 
 template <int KG>
@@ -97,20 +115,22 @@ struct LaneConsts {
 template <int KG>
 __host__ __device__ constexpr int q_row_len() { return 32 * KG + 40; }
 
-// One DP row.  SHORT: this row allows dwell mv-1 (masked row of the second pass).
+// One DP row at pipeline phase PH (leaves the state at phase PH+1).
+// SHORT: this row allows dwell mv-1 (masked row of the second pass).
 // BAND: the end band is active (caller.py:223-224).
-template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
+//   Qpub = &Q[lane] of this row's published buffer, Qrow = the buffer itself
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, int PH>
 __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc, const double x,
-                                       double *__restrict__ Q, const int lane,
-                                       uint32_t *__restrict__ dir_row) {
+                                       double *__restrict__ Qpub, const double *__restrict__ Qrow,
+                                       uint32_t *__restrict__ dir_lane) {
     constexpr int K = KC + KG;
     constexpr int W = (K + 7) / 8;
     const double INF = dinf();
 
     // what other lanes may read this row: my generic states and my chain tail
 #pragma unroll
-    for (int g = 0; g < KG; ++g) Q[g * 32 + lane] = offer<K, MV, SHORT>(s, KC + g);
-    Q[KG * 32 + lane] = offer<K, MV, SHORT>(s, KC - 1);
+    for (int g = 0; g < KG; ++g) Qpub[g * 32] = offer<K, MV, SHORT, PH>(s, KC + g);
+    Qpub[KG * 32] = offer<K, MV, SHORT, PH>(s, KC - 1);
     __syncwarp();
 
     uint32_t codes[W];
@@ -118,11 +138,11 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
     for (int w = 0; w < W; ++w) codes[w] = 0u;
 
     // ---- chain slots: stay or the single incoming edge -----------------------------------
-    double qprev = *reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(Q) + lc.src0);
+    double qprev = *reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(Qrow) + lc.src0);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const double ae = fabs(x - s.v[k]);
-        const double qhere = offer<K, MV, SHORT>(s, k);
+        const double qhere = offer<K, MV, SHORT, PH>(s, k);
         const double stay = s.D[k] + ae;
         const double ch = qprev + ae;
         const bool take = ch < stay;
@@ -134,9 +154,7 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
                 code = 0u;
             }
         }
-#pragma unroll
-        for (int m = MV - 2; m >= 1; --m) s.P[m][k] = s.P[m - 1][k] + ae;
-        s.P[0][k] = stay;
+        advance<K, MV, PH>(s, k, ae, stay);
         s.D[k] = best;
         qprev = qhere;
         codes[k >> 3] |= code << (4 * (k & 7));
@@ -153,7 +171,7 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
 #pragma unroll
         for (int r = 0; r < DEG; ++r) {
             const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
-            const double c = Q[idx] + ae;
+            const double c = Qrow[idx] + ae;
             if (c < best) {
                 best = c;
                 code = static_cast<uint32_t>(r + 1);
@@ -165,32 +183,194 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
                 code = 0u;
             }
         }
-#pragma unroll
-        for (int m = MV - 2; m >= 1; --m) s.P[m][k] = s.P[m - 1][k] + ae;
-        s.P[0][k] = stay;
+        advance<K, MV, PH>(s, k, ae, stay);
         s.D[k] = best;
         codes[k >> 3] |= code << (4 * (k & 7));
     }
 #pragma unroll
-    for (int w = 0; w < W; ++w) dir_row[w * 32 + lane] = codes[w];
+    for (int w = 0; w < W; ++w) dir_lane[w * 32] = codes[w];
+}
+
+// mv-1 consecutive rows: every role returns to its register, nothing has to be moved
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, int PH = 0>
+__device__ __forceinline__ void dp_rows_cycle(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
+                                              const double *__restrict__ xs, double *__restrict__ Qlane,
+                                              const double *__restrict__ Qbase,
+                                              uint32_t *__restrict__ dir_lane) {
+    constexpr int W = (KC + KG + 7) / 8;
+    constexpr int QL = q_row_len<KG>();
+    dp_row<KC, KG, DEG, MV, SHORT, BAND, PH>(s, lc, xs[PH], Qlane + PH * QL, Qbase + PH * QL,
+                                            dir_lane + PH * (W * 32));
+    if constexpr (PH + 1 < MV - 1)
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, PH + 1>(s, lc, xs, Qlane, Qbase, dir_lane);
+}
+
+// a single row from phase 0 back to phase 0 (registers rotated by hand; used for the few rows
+// that do not fill a cycle)
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
+__device__ __forceinline__ void dp_row_single(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc, const double x,
+                                              double *__restrict__ Qlane, const double *__restrict__ Qbase,
+                                              uint32_t *__restrict__ dir_lane) {
+    constexpr int K = KC + KG;
+    dp_row<KC, KG, DEG, MV, SHORT, BAND, 0>(s, lc, x, Qlane, Qbase, dir_lane);
+    __syncwarp();   // the next row publishes into the same buffer
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double last = s.R[MV - 2][k];
+#pragma unroll
+        for (int m = MV - 2; m >= 1; --m) s.R[m][k] = s.R[m - 1][k];
+        s.R[0][k] = last;
+    }
+}
+
+// rows [i0, i1) with one (SHORT, BAND) setting
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
+__device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
+                                           const double *__restrict__ xs, int i0, const int i1,
+                                           double *__restrict__ Qlane, const double *__restrict__ Qbase,
+                                           uint32_t *__restrict__ dir_lane) {
+    constexpr int W = (KC + KG + 7) / 8;
+    constexpr int CY = MV - 1;
+    const double *xp = xs + (i0 & (CH - 1));
+    uint32_t *dp = dir_lane + static_cast<int64_t>(i0) * (W * 32);
+#pragma unroll 1
+    for (; i0 + CY <= i1; i0 += CY) {
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND>(s, lc, xp, Qlane, Qbase, dp);
+        xp += CY;
+        dp += CY * (W * 32);
+    }
+#pragma unroll 1
+    for (; i0 < i1; ++i0) {
+        dp_row_single<KC, KG, DEG, MV, SHORT, BAND>(s, lc, *xp, Qlane, Qbase, dp);
+        xp += 1;
+        dp += W * 32;
+    }
+}
+
+// rows [i0, i1) of one signal tile (all inside one band setting); mask words pick SHORT rows
+template <int KC, int KG, int DEG, int MV, bool BAND>
+__device__ __forceinline__ void dp_tile_rows(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
+                                             const double *__restrict__ xs, int i0, const int i1,
+                                             const uint32_t *__restrict__ mw_ptr, double *__restrict__ Qlane,
+                                             const double *__restrict__ Qbase, uint32_t *__restrict__ dir_lane) {
+    if (!mw_ptr) {
+        dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, i0, i1, Qlane, Qbase, dir_lane);
+        return;
+    }
+    while (i0 < i1) {
+        const int blk_end = min(i1, (i0 | 31) + 1);
+        const uint32_t word = __ldg(mw_ptr + (i0 >> 5));
+        const int n = blk_end - i0;
+        const uint32_t span = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << (i0 & 31);
+        const uint32_t bits = word & span;
+        if (bits == 0u) {
+            dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, i0, blk_end, Qlane, Qbase, dir_lane);
+        } else if (bits == span) {
+            dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, i0, blk_end, Qlane, Qbase, dir_lane);
+        } else {   // mixed block: maximal runs of equal bits
+            int a = i0;
+            while (a < blk_end) {
+                const uint32_t bit = (word >> (a & 31)) & 1u;
+                int b = a + 1;
+                while (b < blk_end && ((word >> (b & 31)) & 1u) == bit) ++b;
+                if (bit) dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, a, b, Qlane, Qbase, dir_lane);
+                else dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, a, b, Qlane, Qbase, dir_lane);
+                a = b;
+            }
+        }
+        i0 = blk_end;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Traceback: follow the stored direction codes from (T-1, endstate) to row 0.  The
+// reference re-derives each step by recomputing the candidates and picking the one that
+// reproduces the stored cost (caller.py:254-299); the winner of the fill reproduces it
+// exactly, so following the fill's arg-min with the same priority (stay, then incoming in
+// list order) visits the same cells.
+//
+// Done by the warp that filled the read, right after the fill.  The walk itself is a chain
+// of dependent steps, so the warp fetches 32 rows at a time (lane t holds the word of row
+// i-t for the lane/word the path is currently in; a word carries the codes of 8 states of
+// that lane, so the window stays valid while the path moves along a chain) and walks the
+// window with shuffles; the trace is written 32 samples at a time.  While this warp waits
+// for its window the SM's other warps keep the FP64 pipe busy with their fills.
+// ------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int T, const uint32_t *dir,
+                                               const uint32_t *mw, int32_t *tr, int32_t *status_slot,
+                                               const int lane) {
+    constexpr int W = (K + 7) / 8;
+    const int mv = A->mv;
+    const int16_t *sop = A->state_of_pos;
+    const int16_t *pred = A->pred_tab;
+    int i = T - 1;
+    int pos = A->end_pos;
+    int st = __ldg(sop + pos);
+    bool failed = false;
+    while (i > 0 && !failed) {
+        const int held_lane = pos / K;
+        int u = pos - held_lane * K;
+        const int held_word = u >> 3;
+        const int row = i - lane;
+        uint32_t w = 0u, mb = 0u;
+        if (row >= mv) w = __ldcg(dir + (static_cast<int64_t>(row) * W + held_word) * 32 + held_lane);
+        if (mw && row >= 0) mb = (__ldg(mw + (row >> 5)) >> (row & 31)) & 1u;
+        int my = -1;
+        int t = 0;
+        while (t < 32 && i - t > 0) {
+            const uint32_t wt = __shfl_sync(FULL, w, t);
+            const uint32_t code = (wt >> (4 * (u & 7))) & 15u;
+            if (lane == t) my = st;
+            if (code == 0u) {
+                t += 1;
+                continue;
+            }
+            const int back = mv - static_cast<int>(__shfl_sync(FULL, mb, t));
+            const int ppos = __ldg(pred + pos * WSTR_PRED_STRIDE + static_cast<int>(code));
+            if (i - t < back || ppos < 0) {
+                failed = true;
+                break;
+            }
+            const int pst = __ldg(sop + ppos);
+            if (lane > t && lane < t + back) my = pst;
+            for (int r = 32; r < t + back; ++r)       // the skip runs past the window (at most mv-1 rows)
+                if (lane == 0 && r > t) tr[i - r] = pst;
+            t += back;
+            pos = ppos;
+            st = pst;
+            const int nl = pos / K;
+            u = pos - nl * K;
+            if (nl != held_lane || (u >> 3) != held_word) break;   // the window no longer covers the path
+        }
+        if (lane < t && row > 0) tr[row] = my;
+        i -= t;
+    }
+    if (lane == 0) {
+        if (failed) *status_slot = WSTR_READ_BACKTRACK;
+        else tr[0] = st;
+    }
 }
 
 // per-warp shared memory: [sig 2 x CH f64][published rows 2 x q_row_len f64][2 mbarriers]
-template <int KG>
+template <int KG, int MV>
 struct alignas(16) FillSmem {
     double sig[2][CH];
-    double Q[2][q_row_len<KG>()];
+    double Q[MV - 1][q_row_len<KG>()];   // one published buffer per pipeline phase
     uint64_t bar[2];
 };
 
+#ifndef WSTR_K8_BLOCKS
+#define WSTR_K8_BLOCKS 4
+#endif
 template <int KC, int KG, int DEG, int MV>
-__global__ void __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 8 ? 4 : (KC + KG <= 12 ? 3 : 2)))
+__global__ void __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 8 ? WSTR_K8_BLOCKS : (KC + KG <= 12 ? 3 : 2)))
 dtw_fill_kernel(const FillParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int K = KC + KG;
     constexpr int W = (K + 7) / 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FillSmem<KG> &sm = reinterpret_cast<FillSmem<KG> *>(smem_raw)[warp];
+    FillSmem<KG, MV> &sm = reinterpret_cast<FillSmem<KG, MV> *>(smem_raw)[warp];
     const double INF = dinf();
 
     if (lane == 0) {
@@ -198,7 +378,7 @@ dtw_fill_kernel(const FillParams p) {
         mbar_init(&sm.bar[1], 1);
         fence_barrier_init();
     }
-    for (int e = lane; e < 2 * q_row_len<KG>(); e += 32) (&sm.Q[0][0])[e] = INF;   // incl. the +inf cell
+    for (int e = lane; e < (MV - 1) * q_row_len<KG>(); e += 32) (&sm.Q[0][0])[e] = INF;   // incl. the +inf cell
     __syncwarp();
     uint32_t uses0 = 0, uses1 = 0;   // completed phases of the two tile barriers
 
@@ -257,7 +437,7 @@ dtw_fill_kernel(const FillParams p) {
             for (int k = 0; k < K; ++k) {
                 s.D[k] = INF;
 #pragma unroll
-                for (int mm = 0; mm < MV - 1; ++mm) s.P[mm][k] = INF;
+                for (int mm = 0; mm < MV - 1; ++mm) s.R[mm][k] = INF;
             }
             for (int c = 0; c <= MV; ++c) {
                 const int pos = A->init_pos[c];
@@ -268,7 +448,7 @@ dtw_fill_kernel(const FillParams p) {
                     if (pos == lane * K + k) {
                         double acc = d0;
                         for (int t = 1; t <= MV - 1; ++t) acc = acc + fabs(x0[t] - s.v[k]);
-                        s.P[MV - 2][k] = acc;   // P_{mv-1}[0]
+                        s.R[MV - 2][k] = acc;   // P_{mv-1}[0] (phase 0)
                     }
                 }
             }
@@ -276,14 +456,10 @@ dtw_fill_kernel(const FillParams p) {
 
         const int band_start = max(A->th1, T - A->band6 + 1);
         const uint32_t *mw_ptr = p.maskbits ? p.maskbits + m.mask_off : nullptr;
-        uint32_t mw = 0u, mw_next = 0u;
-        const int nwords = (T + 31) >> 5;
-        int mblock = MV >> 5;            // 32-row block whose mask word is in mw
-        if (mw_ptr) {
-            mw = __ldg(mw_ptr + mblock);
-            if (mblock + 1 < nwords) mw_next = __ldg(mw_ptr + mblock + 1);
-        }
         uint32_t *dir = p.dir + m.dir_off;
+        uint32_t *dir_lane = dir + lane;
+        double *Qlane = &sm.Q[0][0] + lane;
+        const double *Qbase = &sm.Q[0][0];
 
         for (int c = 0; c < nchunks; ++c) {
             if (c > 0) {
@@ -300,28 +476,11 @@ dtw_fill_kernel(const FillParams p) {
             const double *xs = sm.sig[c & 1];
             const int i_begin = c == 0 ? MV : c * CH;
             const int i_end = min(T, (c + 1) * CH);
-            for (int i = i_begin; i < i_end; ++i) {
-                if (mw_ptr && (i >> 5) != mblock) {   // next mask word, fetched one block ahead
-                    mblock = i >> 5;
-                    mw = mw_next;
-                    if (mblock + 1 < nwords) mw_next = __ldg(mw_ptr + mblock + 1);
-                }
-                const double x = xs[i & (CH - 1)];
-                const bool shortrow = (mw >> (i & 31)) & 1u;
-                double *Q = sm.Q[i & 1];
-                uint32_t *dir_row = dir + static_cast<int64_t>(i) * (W * 32);
-                if (i < band_start) {
-                    if (shortrow)
-                        dp_row<KC, KG, DEG, MV, true, false>(s, lc, x, Q, lane, dir_row);
-                    else
-                        dp_row<KC, KG, DEG, MV, false, false>(s, lc, x, Q, lane, dir_row);
-                } else {
-                    if (shortrow)
-                        dp_row<KC, KG, DEG, MV, true, true>(s, lc, x, Q, lane, dir_row);
-                    else
-                        dp_row<KC, KG, DEG, MV, false, true>(s, lc, x, Q, lane, dir_row);
-                }
-            }
+            const int i_mid = min(max(band_start, i_begin), i_end);   // rows from here on are banded
+            if (i_begin < i_mid)
+                dp_tile_rows<KC, KG, DEG, MV, false>(s, lc, xs, i_begin, i_mid, mw_ptr, Qlane, Qbase, dir_lane);
+            if (i_mid < i_end)
+                dp_tile_rows<KC, KG, DEG, MV, true>(s, lc, xs, i_mid, i_end, mw_ptr, Qlane, Qbase, dir_lane);
             __syncwarp();                          // every lane is done with this tile
             if (c + 2 < nchunks) issue(c + 2);     // refill it
         }
@@ -333,64 +492,15 @@ dtw_fill_kernel(const FillParams p) {
                 if (ep == lane * K + k) p.end_cost[m.read] = s.D[k];
         }
         if (lane == 0) p.status[m.read] = WSTR_READ_OK;
+        __syncwarp();   // this warp's direction words are visible to all of its lanes
+        traceback_warp<K>(A, T, dir, mw_ptr, p.trace + m.sig_off, p.status + m.read, lane);
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// Traceback: follow the stored direction codes from (T-1, endstate) to row 0.  The
-// reference re-derives each step by recomputing the candidates and picking the one that
-// reproduces the stored cost (caller.py:254-299); the winner of the fill reproduces it
-// exactly, so following the fill's arg-min with the same priority (stay, then incoming in
-// list order) visits the same cells.  One thread per read.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) traceback_kernel(const TraceParams p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.n) return;
-    const ReadMeta m = p.meta[idx];
-    if (p.status[m.read] != WSTR_READ_OK) return;
-    const DevAutomaton *A = p.auts + m.aut;
-    const int K = A->K, W = A->W, mv = A->mv;
-    const int16_t *sop = A->state_of_pos;
-    const int16_t *pred = A->pred_tab;
-    const uint32_t *dir = p.dir + m.dir_off;
-    const uint32_t *mw = p.maskbits ? p.maskbits + m.mask_off : nullptr;
-    int32_t *tr = p.trace + m.sig_off;
-
-    int i = m.T - 1;
-    int pos = A->end_pos;
-    int st = sop[pos];
-    while (i > 0) {
-        const int lane = pos / K, k = pos - lane * K;
-        uint32_t code = 0u;
-        if (i >= mv) {   // rows 1..mv-1 are never filled: the reference keeps them at +inf
-            const uint32_t word = dir[(static_cast<int64_t>(i) * W + (k >> 3)) * 32 + lane];
-            code = (word >> (4 * (k & 7))) & 15u;
-        }
-        tr[i] = st;
-        if (code == 0u) {
-            i -= 1;
-            continue;
-        }
-        int back = mv;
-        if (mw && ((mw[i >> 5] >> (i & 31)) & 1u)) back = mv - 1;
-        const int ppos = pred[pos * WSTR_PRED_STRIDE + static_cast<int>(code)];
-        if (i < back || ppos < 0) {
-            p.status[m.read] = WSTR_READ_BACKTRACK;
-            return;
-        }
-        const int pst = sop[ppos];
-        for (int r = 1; r < back; ++r) tr[i - r] = pst;
-        i -= back;
-        pos = ppos;
-        st = pst;
-    }
-    tr[0] = st;
 }
 
 template <int KC, int KG, int DEG, int MV>
 int launch_fill_t(const FillParams &p, cudaStream_t s) {
     static int grid_cap = 0;
-    const int smem = static_cast<int>(sizeof(FillSmem<KG>)) * WSTR_WARPS_PER_CTA;
+    const int smem = static_cast<int>(sizeof(FillSmem<KG, MV>)) * WSTR_WARPS_PER_CTA;
     if (grid_cap == 0) {
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -433,12 +543,4 @@ int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaS
     WSTR_CASE(12, 4, 4)
 #undef WSTR_CASE
     return WSTR_ERR_UNSUPPORTED;
-}
-
-int wstr_launch_traceback(const TraceParams &p, cudaStream_t s) {
-    if (p.n <= 0) return WSTR_OK;
-    const int threads = 128;
-    traceback_kernel<<<(p.n + threads - 1) / threads, threads, 0, s>>>(p);
-    WSTR_CUDA(cudaGetLastError());
-    return WSTR_OK;
 }

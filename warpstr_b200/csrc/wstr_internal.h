@@ -52,18 +52,9 @@ struct FillParams {
     const double *signal;
     const uint32_t *maskbits;    // may be NULL
     uint32_t *dir;               // direction-bit workspace
+    int32_t *trace;              // state index per sample, same offsets as the signal
     double *end_cost;            // may be NULL; indexed by ReadMeta.read
     int32_t *status;             // indexed by ReadMeta.read
-};
-
-struct TraceParams {
-    const DevAutomaton *auts;
-    const ReadMeta *meta;
-    int32_t n;
-    const uint32_t *maskbits;
-    const uint32_t *dir;
-    int32_t *trace;              // same offsets as the signal
-    int32_t *status;
 };
 
 struct wstr_automaton {
@@ -89,4 +80,3 @@ int wstr_set_cuda_error(cudaError_t e, const char *where);
 
 // kernels / launchers (dtw.cu)
 int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
-int wstr_launch_traceback(const TraceParams &p, cudaStream_t s);
