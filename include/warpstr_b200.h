@@ -123,6 +123,57 @@ int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automata,
                     int32_t n_reads, void *d_workspace, int64_t workspace_bytes,
                     int32_t *d_trace, double *d_end_cost, int32_t *d_status, void *stream);
 
+/* ---- whole per-read call --------------------------------------------------------------------------
+ * Replaces WarpSTR.run (src/caller/caller.py:117-149) for a batch: first pass, per-run statistics
+ * and spline rescale, bad-repeat mask, second pass on the rescaled signal, state-wise costs and
+ * decoded sequences -- everything between CallerWrapper.run receiving the workload
+ * (src/caller/wrapper.py:104-120) and CallerResult.  Device-resident from the signal in to the
+ * per-read results out.
+ */
+typedef struct {
+    int32_t min_values_per_state;   /* tr_calling_config.min_values_per_state (= the automata's) */
+    int32_t states_in_segment;      /* tr_calling_config.states_in_segment */
+    double threshold;               /* rescaling.threshold */
+    double max_std;                 /* rescaling.max_std */
+    int32_t method;                 /* rescaling.method: 0 mean; 1 median is WSTR_ERR_UNSUPPORTED here */
+    int32_t reps_as_one;            /* rescaling.reps_as_one: must be 0 here */
+} wstr_call_params;
+
+typedef struct {
+    int32_t *d_len1;        /* len(CallerResult.seq)       -> overview column 'orig'    */
+    int32_t *d_len2;        /* len(CallerResult.resc_seq)  -> overview column 'results' */
+    double *d_cost1;        /* CallerResult.cost           -> 'dtw_cost1' */
+    double *d_cost2;        /* CallerResult.resc_cost      -> 'dtw_cost2' */
+    int32_t *d_status;      /* WSTR_READ_* per read */
+    uint8_t *d_seq1;        /* optional (NULL ok): CallerResult.seq characters, read r at seq_off[r] */
+    uint8_t *d_seq2;        /* optional: CallerResult.resc_seq characters */
+    const int64_t *seq_off; /* host; byte offsets, capacity per read >= lengths[r]/(mv-1) + 16 */
+    int32_t *d_trace1;      /* optional: first-pass trace, same offsets as the signal */
+    int32_t *d_trace2;      /* optional: second-pass trace */
+    double *d_rescaled;     /* optional: rescaled signal, same offsets as the signal */
+} wstr_call_outputs;
+
+/* workspace for processing the whole batch in one wave; anything >= the size for the largest
+ * single read works (more waves) */
+int64_t wstr_call_workspace_bytes(wstr_automaton *const *automata, int32_t n_automata,
+                                  const int32_t *read_automaton, const int32_t *lengths,
+                                  int32_t n_reads);
+/* read_reverse[r] != 0: the read is on the reverse strand (its sequence is reverse-complemented,
+ * caller.py:187).  Other arguments as for wstr_warp_batch. */
+int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,
+                    const int32_t *read_automaton, const uint8_t *read_reverse,
+                    const double *d_signal, const int64_t *sig_off, const int32_t *lengths,
+                    int32_t n_reads, const wstr_call_params *params, void *d_workspace,
+                    int64_t workspace_bytes, const wstr_call_outputs *out, void *stream);
+
+/* ---- kernel timing ------------------------------------------------------------------------------
+ * When enabled, every kernel launch of this library is bracketed by CUDA events on the launching
+ * stream.  wstr_profile_read waits for them and returns, per category (0 DP fill + traceback,
+ * 1 mid-stage, 2 normalisation, 3 pore lookup), the summed device time in ms and the number of
+ * launches since the last read. */
+int wstr_profile_enable(int32_t on);
+int wstr_profile_read(double *ms, int32_t *launches, int32_t n_categories);
+
 /* ---- measurement helper ---------------------------------------------------------------------
  * Times a dependent-free stream of FP64 adds on every SM (the pipe the DP is bound by) and
  * returns the achieved rate in 1e12 DADD/s (lane operations); used by bench.py as the

@@ -118,3 +118,39 @@ def test_full_call_matches_oracle(engine, oracle_c):
             assert got.seq == want.seq and got.resc_seq == want.resc_seq
             assert got.cost == pytest.approx(want.cost, rel=1e-9)
             assert got.resc_cost == pytest.approx(want.resc_cost, rel=1e-9)
+
+
+@pytest.mark.parametrize('name', ['AAAT', 'HD', 'FMR1', 'DM2', 'CAN'])
+def test_device_call_intermediates_match_oracle(engine, oracle_c, name):
+    """wstr_call_batch end to end on the device: both traces identical, the rescaled signal
+    bit-identical to scipy's splev of splrep(s=m), lengths / sequences exact, costs bit-equal
+    (numpy pairwise-sum order is reproduced)."""
+    locus, stas, ids, reads = _setup(engine, name, 6, seed=17, noise=0.2)
+    sigs = [r.signal for r in reads]
+    aut = [ids[int(r.reverse)] for r in reads]
+    rev = [r.reverse for r in reads]
+    packed = engine.upload(sigs, aut, rev)
+    o = engine.call_packed(*packed, want_debug=True)
+    off, lengths = packed[1], packed[2]
+    assert not o['status'].cpu().numpy().any()
+    t1, t2, resc = o['trace1'].cpu().numpy(), o['trace2'].cpu().numpy(), o['rescaled'].cpu().numpy()
+    res = engine.results_from(o, sigs, aut, rev)
+    for n, r in enumerate(reads):
+        tb = co.tables_from(stas[int(r.reverse)])
+        want = co.run_read(r.signal, tb, 110, r.reverse, impl='c')
+        a, ln = int(off[n]), int(lengths[n])
+        assert np.array_equal(t1[a:a + ln], want.trace1), (name, n)
+        assert np.array_equal(resc[a:a + ln], want.rescaled), (name, n)
+        assert np.array_equal(t2[a:a + ln], want.trace2), (name, n)
+        assert res[n].seq == want.seq and res[n].resc_seq == want.resc_seq
+        assert res[n].cost == want.cost and res[n].resc_cost == want.resc_cost
+
+
+def test_device_and_host_engines_agree(engine):
+    locus, stas, ids, reads = _setup(engine, 'HD', 24, seed=29, noise=0.3)
+    args = ([r.signal for r in reads], [ids[int(r.reverse)] for r in reads], [r.reverse for r in reads])
+    dev = engine.call_batch(*args, engine='gpu')
+    host = engine.call_batch(*args, engine='host')
+    for d, h in zip(dev, host):
+        assert d.seq == h.seq and d.resc_seq == h.resc_seq
+        assert d.cost == pytest.approx(h.cost, rel=1e-12) and d.resc_cost == pytest.approx(h.resc_cost, rel=1e-12)

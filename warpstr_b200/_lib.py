@@ -26,6 +26,19 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_vp = ctypes.c_void_p
 
+class CallParams(ctypes.Structure):
+    _fields_ = [('min_values_per_state', ctypes.c_int32), ('states_in_segment', ctypes.c_int32),
+                ('threshold', ctypes.c_double), ('max_std', ctypes.c_double),
+                ('method', ctypes.c_int32), ('reps_as_one', ctypes.c_int32)]
+
+
+class CallOutputs(ctypes.Structure):
+    _fields_ = [('d_len1', ctypes.c_void_p), ('d_len2', ctypes.c_void_p), ('d_cost1', ctypes.c_void_p),
+                ('d_cost2', ctypes.c_void_p), ('d_status', ctypes.c_void_p), ('d_seq1', ctypes.c_void_p),
+                ('d_seq2', ctypes.c_void_p), ('seq_off', ctypes.POINTER(ctypes.c_int64)),
+                ('d_trace1', ctypes.c_void_p), ('d_trace2', ctypes.c_void_p), ('d_rescaled', ctypes.c_void_p)]
+
+
 _SIGNATURES = {
     'wstr_version': (ctypes.c_int, []),
     'wstr_error_string': (ctypes.c_char_p, [ctypes.c_int]),
@@ -48,6 +61,13 @@ _SIGNATURES = {
                                        c_vp, c_i64p, ctypes.c_int32, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp,
                                        c_vp]),
     'wstr_measure_fp64_add_rate': (ctypes.c_int, [c_f64p, c_vp]),
+    'wstr_call_workspace_bytes': (ctypes.c_int64, [ctypes.POINTER(c_vp), ctypes.c_int32, c_i32p, c_i32p,
+                                                   ctypes.c_int32]),
+    'wstr_call_batch': (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int32, c_i32p, c_u8p, c_vp, c_i64p, c_i32p,
+                                       ctypes.c_int32, ctypes.POINTER(CallParams), c_vp, ctypes.c_int64,
+                                       ctypes.POINTER(CallOutputs), c_vp]),
+    'wstr_profile_enable': (ctypes.c_int, [ctypes.c_int32]),
+    'wstr_profile_read': (ctypes.c_int, [c_f64p, c_i32p, ctypes.c_int32]),
 }
 
 
@@ -227,3 +247,45 @@ def measure_fp64_add_rate(stream=None) -> float:
     out = ctypes.c_double(0.0)
     check(lib().wstr_measure_fp64_add_rate(ctypes.byref(out), _stream_ptr(stream)), 'wstr_measure_fp64_add_rate')
     return float(out.value)
+
+
+def call_workspace_bytes(automata: Sequence[DeviceAutomaton], read_automaton, lengths) -> int:
+    ra = _np(read_automaton, np.int32)
+    ln = _np(lengths, np.int32)
+    n = lib().wstr_call_workspace_bytes(_handles(automata), len(automata), _ptr(ra, c_i32p), _ptr(ln, c_i32p),
+                                        int(ln.shape[0]))
+    if n < 0:
+        check(int(n), 'wstr_call_workspace_bytes')
+    return int(n)
+
+
+def call_batch(automata: Sequence[DeviceAutomaton], read_automaton, read_reverse, d_signal, sig_off, lengths,
+               params: CallParams, d_workspace, d_len1, d_len2, d_cost1, d_cost2, d_status, d_seq1=None,
+               d_seq2=None, seq_off=None, d_trace1=None, d_trace2=None, d_rescaled=None, stream=None) -> None:
+    ra = _np(read_automaton, np.int32)
+    rv = _np(read_reverse, np.uint8)
+    so = _np(sig_off, np.int64)
+    ln = _np(lengths, np.int32)
+    qo = _np(seq_off, np.int64) if seq_off is not None else None
+    out = CallOutputs(_dptr(d_len1), _dptr(d_len2), _dptr(d_cost1), _dptr(d_cost2), _dptr(d_status),
+                      _dptr(d_seq1), _dptr(d_seq2), _ptr(qo, c_i64p) if qo is not None else None,
+                      _dptr(d_trace1), _dptr(d_trace2), _dptr(d_rescaled))
+    rc = lib().wstr_call_batch(
+        _handles(automata), len(automata), _ptr(ra, c_i32p), _ptr(rv, c_u8p), _dptr(d_signal), _ptr(so, c_i64p),
+        _ptr(ln, c_i32p), int(ln.shape[0]), ctypes.byref(params), _dptr(d_workspace),
+        int(d_workspace.numel() * d_workspace.element_size()), ctypes.byref(out), _stream_ptr(stream))
+    check(rc, 'wstr_call_batch')
+
+
+PROFILE_CATEGORIES = ('dp_fill_traceback', 'midstage', 'normalize', 'pore_lookup')
+
+
+def profile_enable(on: bool = True) -> None:
+    check(lib().wstr_profile_enable(1 if on else 0), 'wstr_profile_enable')
+
+
+def profile_read() -> dict:
+    ms = np.zeros(4, dtype=np.float64)
+    cnt = np.zeros(4, dtype=np.int32)
+    check(lib().wstr_profile_read(_ptr(ms, c_f64p), _ptr(cnt, c_i32p), 4), 'wstr_profile_read')
+    return {name: {'ms': float(ms[i]), 'launches': int(cnt[i])} for i, name in enumerate(PROFILE_CATEGORIES)}

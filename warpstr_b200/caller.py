@@ -168,10 +168,91 @@ class CallerEngine:
         return reverse_complement(seq) if reverse else seq
 
     def call_batch(self, signals: Sequence[np.ndarray], aut_ids: Sequence[int],
-                   reverse: Sequence[bool]) -> List[CallerResult]:
-        """WarpSTR.run for a batch (caller.py:117-149): pass 1 on the GPU, rescale + mask,
-        pass 2 on the GPU, costs and sequences."""
+                   reverse: Sequence[bool], engine: Optional[str] = None) -> List[CallerResult]:
+        """WarpSTR.run for a batch (caller.py:117-149).  ``engine='gpu'`` (default for the
+        default rescaling configuration) keeps everything on the device (wstr_call_batch);
+        ``engine='host'`` runs the two DP passes on the GPU and the stage between them in
+        numpy/scipy (needed for ``reps_as_one`` / ``method: median``)."""
         signals = [np.ascontiguousarray(s, dtype=np.float64) for s in signals]
+        gpu_ok = (not self.rc.reps_as_one) and self.rc.method == 'mean'
+        engine = engine or ('gpu' if gpu_ok else 'host')
+        if engine == 'host':
+            return self._call_batch_host(signals, aut_ids, reverse)
+        if not gpu_ok:
+            raise _lib.WarpstrError('the device mid-stage covers reps_as_one=False, method=mean only')
+        res = self.call_packed(*self.upload(signals, aut_ids, reverse))
+        return self.results_from(res, signals, aut_ids, reverse)
+
+    # -- device-resident form -----------------------------------------------------------------------
+    def upload(self, signals: Sequence[np.ndarray], aut_ids: Sequence[int], reverse: Sequence[bool]):
+        """Host -> device copy of a batch.  Returns the tuple ``call_packed`` takes."""
+        host, off, lengths = pack_signals(signals)
+        d_sig = host.to(self.device, non_blocking=True)
+        return d_sig, off, lengths, np.asarray(aut_ids, dtype=np.int32), np.asarray(reverse, dtype=np.uint8)
+
+    def call_packed(self, d_sig, off, lengths, aut, rev, want_seq: bool = True, want_debug: bool = False):
+        """wstr_call_batch on device-resident signals.  Returns a dict of device tensors
+        (len1, len2, cost1, cost2, status[, seq1, seq2, seq_off])."""
+        import torch
+        n = len(lengths)
+        with torch.cuda.device(self.device):
+            need = _lib.call_workspace_bytes(self.automata, aut, lengths)
+            ws = self._workspace(need)
+            o = dict(
+                len1=torch.empty(n, dtype=torch.int32, device=self.device),
+                len2=torch.empty(n, dtype=torch.int32, device=self.device),
+                cost1=torch.empty(n, dtype=torch.float64, device=self.device),
+                cost2=torch.empty(n, dtype=torch.float64, device=self.device),
+                status=torch.zeros(n, dtype=torch.int32, device=self.device))
+            seq_off = None
+            if want_seq:
+                cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
+                seq_off = np.zeros(n, dtype=np.int64)
+                seq_off[1:] = np.cumsum(cap[:-1])
+                total = int(cap.sum())
+                o['seq1'] = torch.empty(total, dtype=torch.uint8, device=self.device)
+                o['seq2'] = torch.empty(total, dtype=torch.uint8, device=self.device)
+                o['seq_off'] = seq_off
+            if want_debug:   # intermediate products, for the parity tests
+                o['trace1'] = torch.empty(d_sig.numel(), dtype=torch.int32, device=self.device)
+                o['trace2'] = torch.empty(d_sig.numel(), dtype=torch.int32, device=self.device)
+                o['rescaled'] = torch.empty(d_sig.numel(), dtype=torch.float64, device=self.device)
+            params = _lib.CallParams(self.cc.min_values_per_state, self.cc.states_in_segment,
+                                     float(self.rc.threshold), float(self.rc.max_std), 0, 0)
+            _lib.call_batch(self.automata, aut, rev, d_sig, off, lengths, params, ws, o['len1'], o['len2'],
+                            o['cost1'], o['cost2'], o['status'], o.get('seq1'), o.get('seq2'), seq_off,
+                            o.get('trace1'), o.get('trace2'), o.get('rescaled'))
+        return o
+
+    def results_from(self, o, signals, aut_ids, reverse) -> List[CallerResult]:
+        """Device results -> CallerResult list; reads the device could not finish (status != 0)
+        are redone on the host path or raise what the reference raises."""
+        status = o['status'].cpu().numpy()
+        len1, len2 = o['len1'].cpu().numpy(), o['len2'].cpu().numpy()
+        cost1, cost2 = o['cost1'].cpu().numpy(), o['cost2'].cpu().numpy()
+        seq1, seq2 = o['seq1'].cpu().numpy(), o['seq2'].cpu().numpy()
+        off = o['seq_off']
+        out: List[Optional[CallerResult]] = []
+        redo = []
+        for r in range(len(status)):
+            if status[r] == 0:
+                a = int(off[r])
+                out.append(CallerResult(seq=seq1[a:a + len1[r]].tobytes().decode('ascii'), cost=float(cost1[r]),
+                                        resc_seq=seq2[a:a + len2[r]].tobytes().decode('ascii'),
+                                        resc_cost=float(cost2[r])))
+            else:
+                out.append(None)
+                redo.append(r)
+        if redo:
+            # status 5 (spline needs interior knots) is a legitimate host evaluation; every other
+            # status is an exception in the reference, which the host path raises with its type
+            fixed = self._call_batch_host([signals[r] for r in redo], [aut_ids[r] for r in redo],
+                                          [reverse[r] for r in redo])
+            for r, res in zip(redo, fixed):
+                out[r] = res
+        return out
+
+    def _call_batch_host(self, signals, aut_ids, reverse) -> List[CallerResult]:
         traces1 = self.warp_batch(signals, aut_ids)
         first = []
         for s, a, t in zip(signals, aut_ids, traces1):

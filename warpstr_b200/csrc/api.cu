@@ -36,6 +36,63 @@ extern "C" const char *wstr_error_string(int code) {
 }
 
 // ------------------------------------------------------------------------------------------
+// kernel timing (CUDA events on the launching stream)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct ProfSpan {
+    int cat;
+    cudaEvent_t a, b;
+};
+bool g_prof_on = false;
+std::vector<ProfSpan> g_prof_spans;
+}  // namespace
+
+void wstr_prof_begin(int cat, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfSpan sp;
+    sp.cat = cat;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, s);
+    g_prof_spans.push_back(sp);
+}
+
+void wstr_prof_end(cudaStream_t s) {
+    if (!g_prof_on || g_prof_spans.empty()) return;
+    cudaEventRecord(g_prof_spans.back().b, s);
+}
+
+extern "C" int wstr_profile_enable(int32_t on) {
+    g_prof_on = on != 0;
+    return WSTR_OK;
+}
+
+extern "C" int wstr_profile_read(double *ms, int32_t *launches, int32_t n) {
+    if (!ms || !launches || n <= 0) return WSTR_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n; ++i) {
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+    for (ProfSpan &sp : g_prof_spans) {
+        cudaError_t e = cudaEventSynchronize(sp.b);
+        float t = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, sp.a, sp.b);
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+        if (e != cudaSuccess) {
+            g_prof_spans.clear();
+            return wstr_set_cuda_error(e, "wstr_profile_read");
+        }
+        if (sp.cat >= 0 && sp.cat < n) {
+            ms[sp.cat] += t;
+            launches[sp.cat] += 1;
+        }
+    }
+    g_prof_spans.clear();
+    return WSTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // automaton layout (see dtw.cu)
 //
 // A "chain link" j -> t is an edge where j has no other successor and t no other predecessor.
@@ -419,11 +476,11 @@ extern "C" int64_t wstr_warp_workspace_bytes(wstr_automaton *const *automata, in
     return (int64_t)w.fixed_end + words * 4 + 256;
 }
 
-extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automata,
-                               const int32_t *read_automaton, const double *d_signal, const int64_t *sig_off,
-                               const int32_t *lengths, const uint32_t *d_maskbits, const int64_t *mask_off,
-                               int32_t n_reads, void *d_workspace, int64_t workspace_bytes, int32_t *d_trace,
-                               double *d_end_cost, int32_t *d_status, void *stream) {
+static int warp_pass(wstr_automaton *const *automata, int32_t n_automata, const int32_t *read_automaton,
+                     const double *d_signal, const int64_t *sig_off, const int32_t *lengths,
+                     const uint32_t *d_maskbits, const int64_t *mask_off, int32_t n_reads, void *d_workspace,
+                     int64_t workspace_bytes, int32_t *d_trace, double *d_end_cost, int32_t *d_status,
+                     void *stream, int respect_status) {
     if (!automata || n_automata <= 0 || n_reads < 0 || !d_signal || !sig_off || !lengths || !d_workspace ||
         !d_trace || !d_status)
         return WSTR_ERR_INVALID_ARGUMENT;
@@ -515,7 +572,10 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
             fp.trace = d_trace;
             fp.end_cost = d_end_cost;
             fp.status = d_status;
+            fp.respect_status = respect_status;
+            wstr_prof_begin(0, s);
             int rc = wstr_launch_fill(ref.KC, ref.KG, ref.DEG, mv, fp, s);
+            wstr_prof_end(s);
             if (rc != WSTR_OK) return rc;
             ++cls;
         }
@@ -526,4 +586,187 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
         }
     }
     return WSTR_OK;
+}
+
+extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automata,
+                               const int32_t *read_automaton, const double *d_signal, const int64_t *sig_off,
+                               const int32_t *lengths, const uint32_t *d_maskbits, const int64_t *mask_off,
+                               int32_t n_reads, void *d_workspace, int64_t workspace_bytes, int32_t *d_trace,
+                               double *d_end_cost, int32_t *d_status, void *stream) {
+    return warp_pass(automata, n_automata, read_automaton, d_signal, sig_off, lengths, d_maskbits, mask_off,
+                     n_reads, d_workspace, workspace_bytes, d_trace, d_end_cost, d_status, stream, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// whole per-read call: pass 1 -> mid-stage -> pass 2 -> mid-stage
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct CallPlan {
+    size_t o_queue, o_mauts, o_reads, o_state, o_cubic, o_resc, o_trace, o_mask, o_scratch, o_warp;
+    int64_t extent;       // elements of the signal buffer in use
+    int64_t mask_words;
+    int64_t scratch_bytes;
+};
+
+CallPlan plan_call(int n_automata, int n_reads, const int64_t *sig_off, const int32_t *lengths, int mv,
+                   bool own_resc, bool own_trace) {
+    CallPlan c;
+    c.extent = 0;
+    c.mask_words = 0;
+    c.scratch_bytes = 0;
+    int64_t run_off = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        const int64_t so = sig_off ? sig_off[r] : run_off;
+        c.extent = std::max<int64_t>(c.extent, so + lengths[r] + 2);
+        run_off += ((int64_t)lengths[r] + 1) & ~(int64_t)1;
+        c.mask_words += (lengths[r] + 31) / 32;
+        c.scratch_bytes += wstr_mid_scratch_bytes(lengths[r], mv);
+    }
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    c.o_queue = take(256);
+    c.o_mauts = take(sizeof(MidAutomaton) * (size_t)n_automata);
+    c.o_reads = take(sizeof(MidRead) * (size_t)n_reads);
+    c.o_state = take(sizeof(MidState) * (size_t)n_reads);
+    c.o_cubic = take(sizeof(double) * 8 * (size_t)n_reads);
+    c.o_resc = take(own_resc ? sizeof(double) * (size_t)c.extent : 0);
+    c.o_trace = take(own_trace ? sizeof(int32_t) * (size_t)c.extent : 0);
+    c.o_mask = take(sizeof(uint32_t) * (size_t)(c.mask_words + 1));
+    c.o_scratch = take((size_t)c.scratch_bytes);
+    c.o_warp = off;
+    return c;
+}
+
+}  // namespace
+
+extern "C" int64_t wstr_call_workspace_bytes(wstr_automaton *const *automata, int32_t n_automata,
+                                             const int32_t *read_automaton, const int32_t *lengths,
+                                             int32_t n_reads) {
+    if (!automata || n_automata <= 0 || n_reads < 0 || !lengths) return WSTR_ERR_INVALID_ARGUMENT;
+    const int64_t warp = wstr_warp_workspace_bytes(automata, n_automata, read_automaton, lengths, n_reads);
+    if (warp < 0) return warp;
+    const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true);
+    return (int64_t)c.o_warp + warp;
+}
+
+extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,
+                               const int32_t *read_automaton, const uint8_t *read_reverse,
+                               const double *d_signal, const int64_t *sig_off, const int32_t *lengths,
+                               int32_t n_reads, const wstr_call_params *params, void *d_workspace,
+                               int64_t workspace_bytes, const wstr_call_outputs *out, void *stream) {
+    if (!automata || n_automata <= 0 || n_reads < 0 || !d_signal || !sig_off || !lengths || !params || !out ||
+        !d_workspace || !out->d_len1 || !out->d_len2 || !out->d_cost1 || !out->d_cost2 || !out->d_status)
+        return WSTR_ERR_INVALID_ARGUMENT;
+    if ((out->d_seq1 || out->d_seq2) && !out->seq_off) return WSTR_ERR_INVALID_ARGUMENT;
+    if (n_reads == 0) return WSTR_OK;
+    if (params->method != 0 || params->reps_as_one != 0) return WSTR_ERR_UNSUPPORTED;
+    if (params->states_in_segment < 2) return WSTR_ERR_INVALID_ARGUMENT;
+    const int mv = automata[0]->dev.mv;
+    if (params->min_values_per_state != mv) return WSTR_ERR_INVALID_ARGUMENT;
+    for (int r = 0; r < n_reads; ++r) {
+        const int a = read_automaton ? read_automaton[r] : 0;
+        if (a < 0 || a >= n_automata || lengths[r] < 0 || (sig_off[r] & 1)) return WSTR_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool own_resc = out->d_rescaled == nullptr;
+    const bool own_trace = out->d_trace1 == nullptr || out->d_trace2 == nullptr;
+    const CallPlan c = plan_call(n_automata, n_reads, sig_off, lengths, mv, own_resc, own_trace);
+    if ((int64_t)c.o_warp + (1 << 16) > workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    unsigned char *ws = static_cast<unsigned char *>(d_workspace);
+    int32_t *d_queue = reinterpret_cast<int32_t *>(ws + c.o_queue);
+    MidAutomaton *d_mauts = reinterpret_cast<MidAutomaton *>(ws + c.o_mauts);
+    MidRead *d_reads = reinterpret_cast<MidRead *>(ws + c.o_reads);
+    MidState *d_state = reinterpret_cast<MidState *>(ws + c.o_state);
+    double *d_cubic = reinterpret_cast<double *>(ws + c.o_cubic);
+    double *d_resc = own_resc ? reinterpret_cast<double *>(ws + c.o_resc) : out->d_rescaled;
+    int32_t *d_own_trace = reinterpret_cast<int32_t *>(ws + c.o_trace);
+    int32_t *d_trace1 = out->d_trace1 ? out->d_trace1 : d_own_trace;
+    int32_t *d_trace2 = out->d_trace2 ? out->d_trace2 : d_own_trace;
+    uint32_t *d_mask = reinterpret_cast<uint32_t *>(ws + c.o_mask);
+    unsigned char *d_scratch = ws + c.o_scratch;
+    void *warp_ws = ws + c.o_warp;
+    const int64_t warp_bytes = workspace_bytes - (int64_t)c.o_warp;
+
+    std::vector<MidAutomaton> mauts(n_automata);
+    for (int a = 0; a < n_automata; ++a) {
+        mauts[a].values = automata[a]->d_values;
+        mauts[a].seq_idx = automata[a]->d_seq_idx;
+        mauts[a].rep_mask = automata[a]->d_rep_mask;
+        mauts[a].last_base = automata[a]->d_last_base;
+        mauts[a].flank_length = automata[a]->flank_length;
+        mauts[a].pad_ = 0;
+    }
+    std::vector<MidRead> reads(n_reads);
+    std::vector<int64_t> mask_off(n_reads);
+    int64_t mo = 0, so = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        MidRead &m = reads[r];
+        m.sig_off = sig_off[r];
+        m.mask_off = mo;
+        m.ws_off = so;
+        m.seq_off = out->seq_off ? out->seq_off[r] : -1;
+        m.T = lengths[r];
+        m.aut = read_automaton ? read_automaton[r] : 0;
+        m.read = r;
+        m.reverse = read_reverse ? (read_reverse[r] != 0) : 0;
+        m.run_cap = lengths[r] / (mv > 2 ? mv - 1 : 1) + 16;
+        m.pad_ = 0;
+        mask_off[r] = mo;
+        mo += (lengths[r] + 31) / 32;
+        so += wstr_mid_scratch_bytes(lengths[r], mv);
+    }
+    WSTR_CUDA(cudaMemcpyAsync(d_mauts, mauts.data(), sizeof(MidAutomaton) * n_automata, cudaMemcpyHostToDevice, s));
+    WSTR_CUDA(cudaMemcpyAsync(d_reads, reads.data(), sizeof(MidRead) * n_reads, cudaMemcpyHostToDevice, s));
+
+    // ---- first pass --------------------------------------------------------------------------
+    int rc = warp_pass(automata, n_automata, read_automaton, d_signal, sig_off, lengths, nullptr, nullptr, n_reads,
+                       warp_ws, warp_bytes, d_trace1, nullptr, out->d_status, stream, 0);
+    if (rc != WSTR_OK) return rc;
+    MidParams mp;
+    mp.auts = d_mauts;
+    mp.reads = d_reads;
+    mp.n = n_reads;
+    mp.queue = d_queue;
+    mp.x = d_signal;
+    mp.trace = d_trace1;
+    mp.rescaled = d_resc;
+    mp.maskbits = d_mask;
+    mp.scratch = d_scratch;
+    mp.state = d_state;
+    mp.cubic = d_cubic;
+    mp.len = out->d_len1;
+    mp.cost = out->d_cost1;
+    mp.seq = out->d_seq1;
+    mp.status = out->d_status;
+    mp.mv = mv;
+    mp.sis = params->states_in_segment;
+    mp.threshold = params->threshold;
+    mp.max_std = params->max_std;
+    WSTR_CUDA(cudaMemsetAsync(d_queue, 0, 256, s));
+    wstr_prof_begin(1, s);
+    rc = wstr_launch_midstage(mp, false, s);
+    wstr_prof_end(s);
+    if (rc != WSTR_OK) return rc;
+
+    // ---- second pass on the rescaled signal, masked rows allow the shorter dwell ----------------
+    rc = warp_pass(automata, n_automata, read_automaton, d_resc, sig_off, lengths, d_mask, mask_off.data(), n_reads,
+                   warp_ws, warp_bytes, d_trace2, nullptr, out->d_status, stream, 1);
+    if (rc != WSTR_OK) return rc;
+    mp.x = d_resc;
+    mp.trace = d_trace2;
+    mp.rescaled = nullptr;
+    mp.maskbits = nullptr;
+    mp.len = out->d_len2;
+    mp.cost = out->d_cost2;
+    mp.seq = out->d_seq2;
+    WSTR_CUDA(cudaMemsetAsync(d_queue, 0, 256, s));
+    wstr_prof_begin(1, s);
+    rc = wstr_launch_midstage(mp, true, s);
+    wstr_prof_end(s);
+    return rc;
 }

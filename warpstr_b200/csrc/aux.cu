@@ -51,8 +51,10 @@ extern "C" int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d
     const int threads = 256;
     int64_t blocks = (n_out + threads - 1) / threads;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    wstr_prof_begin(3, static_cast<cudaStream_t>(stream));
     pore_lookup_kernel<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(d_seq, n_out, d_table, k, d_out,
                                                                                        d_bad);
+    wstr_prof_end(static_cast<cudaStream_t>(stream));
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;
 }
@@ -408,7 +410,9 @@ extern "C" int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off
                                        (int)sizeof(NormSmem)));
         attr_set = true;
     }
+    wstr_prof_begin(2, s);
     normalize_kernel<<<grid, NT, sizeof(NormSmem), s>>>(p);
+    wstr_prof_end(s);
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;
 }

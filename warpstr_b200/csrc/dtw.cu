@@ -395,6 +395,7 @@ dtw_fill_kernel(const FillParams p) {
         const ReadMeta m = p.meta[p.order[r]];
         const DevAutomaton *A = p.auts + m.aut;
         const int T = m.T;
+        if (p.respect_status && p.status[m.read] != WSTR_READ_OK) continue;   // failed earlier in the call
         if (T <= MV) {
             if (lane == 0) p.status[m.read] = WSTR_READ_TOO_SHORT;
             continue;

@@ -1,0 +1,563 @@
+// What WarpSTR does with a pass's trace: run statistics, spline rescale, bad-repeat mask,
+// state-wise cost and the decoded sequence.  One warp per read.
+//
+// Replaces, for the default rescaling configuration (reps_as_one False, method mean):
+//   WarpResult.state_transitions / create_alignment   reference src/caller/caller.py:58-96
+//   StateAlignment.good_enough / filter_alignment      :23-39, :316-318
+//   rescale_signal (splrep s=m, splev)                 :304-313
+//   mask_bad_repeats and helpers                       :330-421
+//   the cost lines of WarpSTR.run                      :138-139
+//   WarpSTR._get_sequence                              :178-187
+//
+// Bit-level fidelity.  Means and variances use numpy's pairwise summation order
+// (numpy/_core/src/umath/loops_utils.h.src: n<8 sequential, <=128 eight accumulators, else
+// halves).  splrep(x, y, s=m) is FITPACK curfit (scipy pins 1.6.3; same algorithm in 1.18):
+// its first iteration is the least-squares cubic polynomial on the knots [xb]*4+[xe]*4 and it
+// is accepted whenever its residual fp <= s, which holds for every read whose filtered pairs
+// satisfy |y-x| <= threshold <= 1 (fp <= m*threshold^2).  That iteration (fpcurf's Givens
+// sweep: fpbspl, fpgivs, fprota, fpback) and splev are restated here operation by operation;
+// this file is compiled with -fmad=false, and the host test compares the coefficients with
+// scipy bit for bit.  If fp > s the spline needs interior knots: the read is flagged
+// WSTR_READ_SPLINE_KNOTS and the Python host evaluates it with scipy.
+// One known last-bit difference: the reference squares a standard deviation with pow(x, 2)
+// inside calc_ttest (caller.py:351); glibc's pow differs from x*x in the last bit for about
+// 0.1 % of arguments, so a t statistic can differ by one ulp; that flips a decision only
+// if the statistic is within one ulp of +-3 or of its predecessor.
+#include <math.h>
+
+#include "wstr_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- numpy pairwise summation over f(0..n-1) ---------------------------------------------------
+template <class F>
+__device__ double pairwise_sum(const F &f, int start, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += f(start + i);
+        return res;
+    }
+    if (n <= 128) {
+        double r0 = f(start), r1 = f(start + 1), r2 = f(start + 2), r3 = f(start + 3), r4 = f(start + 4),
+               r5 = f(start + 5), r6 = f(start + 6), r7 = f(start + 7);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+            r0 += f(start + i);
+            r1 += f(start + i + 1);
+            r2 += f(start + i + 2);
+            r3 += f(start + i + 3);
+            r4 += f(start + i + 4);
+            r5 += f(start + i + 5);
+            r6 += f(start + i + 6);
+            r7 += f(start + i + 7);
+        }
+        double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+        for (; i < n; ++i) res += f(start + i);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return pairwise_sum(f, start, n2) + pairwise_sum(f, start + n2, n - n2);
+}
+
+// ---- FITPACK pieces for the single-interval cubic ------------------------------------------------
+// fpbspl with k=3 on knots [xb,xb,xb,xb,xe,xe,xe,xe], interval l=4
+__device__ __forceinline__ void bspl3(double xb, double xe, double x, double *h) {
+    double hh[3];
+    h[0] = 1.0;
+    for (int j = 1; j <= 3; ++j) {
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+        for (int i = 1; i <= j; ++i) {
+            if (xe == xb) {
+                h[i] = 0.0;
+                continue;
+            }
+            const double f = hh[i - 1] / (xe - xb);
+            h[i - 1] = h[i - 1] + f * (xe - x);
+            h[i] = f * (x - xb);
+        }
+    }
+}
+
+__device__ __forceinline__ void givens(double piv, double &ww, double &c, double &s) {
+    const double store = fabs(piv);
+    double dd;
+    if (store >= ww) {
+        const double r = ww / piv;
+        dd = store * sqrt(1.0 + r * r);
+    } else {
+        const double r = piv / ww;
+        dd = ww * sqrt(1.0 + r * r);
+    }
+    c = ww / dd;
+    s = piv / dd;
+    ww = dd;
+}
+
+__device__ __forceinline__ void rotate(double c, double s, double &a, double &b) {
+    const double s1 = a, s2 = b;
+    b = c * s2 + s * s1;
+    a = c * s1 - s * s2;
+}
+
+struct Cubic {
+    double xb, xe, c[4], fp;
+};
+
+// least-squares cubic through (sx[i], sy[i]), i < m, sx ascending: fpcurf's first iteration
+__device__ void lsq_cubic(const double *sx, const double *sy, int m, Cubic &out) {
+    const double xb = sx[0], xe = sx[m - 1];
+    double a[4][4], z[4];
+    for (int i = 0; i < 4; ++i) {
+        z[i] = 0.0;
+        for (int j = 0; j < 4; ++j) a[i][j] = 0.0;
+    }
+    double fp = 0.0;
+    for (int it = 0; it < m; ++it) {
+        const double xi = sx[it];
+        double yi = sy[it];
+        double h[4];
+        bspl3(xb, xe, xi, h);
+        for (int i = 0; i < 4; ++i) {
+            const double piv = h[i];
+            if (piv == 0.0) continue;
+            double c, s;
+            givens(piv, a[i][0], c, s);
+            rotate(c, s, yi, z[i]);
+            if (i == 3) break;
+            int i2 = 0;
+            for (int i1 = i + 1; i1 < 4; ++i1) {
+                ++i2;
+                rotate(c, s, h[i1], a[i][i2]);
+            }
+        }
+        fp = fp + yi * yi;
+    }
+    // fpback, n = 4, bandwidth 4
+    double c[4];
+    c[3] = z[3] / a[3][0];
+    int i = 2;
+    for (int j = 2; j <= 4; ++j) {
+        double store = z[i];
+        const int i1 = j <= 3 ? j - 1 : 3;
+        int mm = i;
+        for (int l = 1; l <= i1; ++l) {
+            ++mm;
+            store = store - c[mm] * a[i][l];
+        }
+        c[i] = store / a[i][0];
+        --i;
+    }
+    out.xb = xb;
+    out.xe = xe;
+    out.fp = fp;
+    for (int q = 0; q < 4; ++q) out.c[q] = c[q];
+}
+
+__device__ __forceinline__ double splev3(const Cubic &cu, double x) {
+    double h[4];
+    bspl3(cu.xb, cu.xe, x, h);
+    double sp = 0.0;
+    for (int j = 0; j < 4; ++j) sp = sp + cu.c[j] * h[j];
+    return sp;
+}
+
+// ---- sliding two-sample statistic (caller.py:347-354), windows x[c-3:c] and x[c:c+3] -----------
+__device__ __forceinline__ void mean_sd3(const double *w, double &mean, double &sd) {
+    mean = ((w[0] + w[1]) + w[2]) / 3.0;
+    const double d0 = w[0] - mean, d1 = w[1] - mean, d2 = w[2] - mean;
+    const double var = ((d0 * d0 + d1 * d1) + d2 * d2) / 3.0;
+    sd = sqrt(var);
+}
+
+__device__ __forceinline__ double tstat(const double *x, int c) {
+    double ma, sa, mb, sb;
+    mean_sd3(x + c - 3, ma, sa);
+    mean_sd3(x + c, mb, sb);
+    double sd = sqrt((sa * sa + sb * sb) / 3.0);
+    if (sd == 0.0) sd = sd + 0.0000001;
+    return (ma - mb) / sd;
+}
+
+// number of detected segment borders minus one in t(c0..c1) (caller.py:357-378)
+__device__ int count_segments(const double *x, int c0, int c1) {
+    int borders = 0;
+    bool rising = false;
+    double prev = tstat(x, c0);
+    for (int c = c0; c <= c1; ++c) {
+        const double t = c == c0 ? prev : tstat(x, c);
+        if (t > 3.0 || t < -3.0) {
+            if ((t > 3.0 && t >= prev) || (t < -3.0 && t <= prev)) {
+                rising = true;
+            } else {
+                if (rising) ++borders;
+                rising = false;
+            }
+        } else if (rising) {
+            ++borders;
+            rising = false;
+        }
+        prev = t;
+    }
+    return borders - 1;
+}
+
+__device__ __forceinline__ int warp_min(int v) {
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint8_t complement(uint8_t b) {
+    switch (b) {
+        case 'A': return 'T';
+        case 'C': return 'G';
+        case 'G': return 'C';
+        case 'T': return 'A';
+        default: return b;
+    }
+}
+
+struct Scratch {
+    int32_t *run_start, *run_state;
+    double *sv, *px, *py, *sx, *sy;
+};
+
+__device__ __forceinline__ Scratch carve(unsigned char *ws, int R) {
+    Scratch s;
+    s.run_start = reinterpret_cast<int32_t *>(ws);   // R+1
+    s.run_state = s.run_start + (R + 1);             // R
+    s.sv = reinterpret_cast<double *>(ws + ((8 * (size_t)R + 4 + 7) / 8) * 8);
+    s.px = s.sv + R;
+    s.py = s.px + R;
+    s.sx = s.py + R;
+    s.sy = s.sx + R;
+    return s;
+}
+
+// Kernel A (one warp per read): run-length view, per-run statistics, filtered pairs sorted by
+// state value, repeat-region borders.
+template <bool SECOND>
+__global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(p.queue, 1);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= p.n) break;
+        const MidRead rd = p.reads[q];
+        if (p.status[rd.read] != WSTR_READ_OK) continue;
+        const MidAutomaton A = p.auts[rd.aut];
+        const int T = rd.T;
+        const double *x = p.x + rd.sig_off;
+        const int32_t *trace = p.trace + rd.sig_off;
+        const int R = rd.run_cap;
+        const Scratch sc = carve(p.scratch + rd.ws_off, R);
+        int32_t *run_start = sc.run_start, *run_state = sc.run_state;
+        int fail = 0;
+
+        // ---- run-length view of the trace (caller.py:58-60) -----------------------------------
+        int n_runs = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            bool head = false;
+            int st = 0;
+            if (t < T) {
+                st = trace[t];
+                head = t == 0 || trace[t - 1] != st;
+            }
+            const unsigned bal = __ballot_sync(FULL, head);
+            if (head) {
+                const int r = n_runs + __popc(bal & ((1u << lane) - 1u));
+                if (r < R) {
+                    run_start[r] = t;
+                    run_state[r] = st;
+                }
+            }
+            n_runs += __popc(bal);
+        }
+        if (n_runs > R) fail = WSTR_READ_SEGMENT;   // cannot happen: a run has >= mv-1 samples
+        if (!fail && lane == 0) run_start[n_runs] = T;
+        __syncwarp();
+
+        // ---- per-run statistics (caller.py:65-96, 23-39) ---------------------------------------
+        int m = 0;   // good pairs
+        if (!fail) {
+            for (int r0 = 0; r0 < n_runs; r0 += 32) {
+                const int r = r0 + lane;
+                bool g = false;
+                double mean = 0.0, expect = 0.0;
+                if (r < n_runs) {
+                    const int a = run_start[r], n = run_start[r + 1] - a;
+                    const double *xs = x + a;
+                    const double sum = pairwise_sum([xs](int i) { return xs[i]; }, 0, n);
+                    mean = sum / (double)n;
+                    expect = A.values[run_state[r]];
+                    sc.sv[r] = mean;
+                    if (n >= p.mv) {
+                        const double ss = pairwise_sum(
+                            [xs, mean](int i) {
+                                const double d = xs[i] - mean;
+                                return d * d;
+                            },
+                            0, n);
+                        const double sd = sqrt(ss / (double)n);
+                        g = sd < p.max_std && fabs(expect - mean) <= p.threshold;
+                    }
+                }
+                const unsigned bal = __ballot_sync(FULL, g);
+                if (g) {
+                    const int k = m + __popc(bal & ((1u << lane) - 1u));
+                    sc.px[k] = mean;
+                    sc.py[k] = expect;
+                }
+                m += __popc(bal);
+            }
+            __syncwarp();
+            if (m <= 3) fail = WSTR_READ_SPLINE;   // splrep: 'm > k must hold'
+        }
+
+        if (!SECOND && !fail) {
+            // ---- stable sort by state value (caller.py:306): rank sort ------------------------------
+            for (int i0 = 0; i0 < m; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < m) {
+                    const double key = sc.px[i];
+                    int rank = 0;
+                    for (int j = 0; j < m; ++j) {
+                        const double o = sc.px[j];
+                        rank += (o < key) || (o == key && j < i);
+                    }
+                    sc.sx[rank] = key;
+                    sc.sy[rank] = sc.py[i];
+                }
+            }
+        }
+
+        // ---- repeat-region borders (caller.py:381-406) -------------------------------------------
+        int start = -1, end = -1, ra = 0, rb = 0, ncuts = 0;
+        if (!fail) {
+            int first = 1 << 30, last = -1;
+            for (int r = lane; r < n_runs; r += 32) {
+                if (A.rep_mask[run_state[r]]) {
+                    first = min(first, r);
+                    last = max(last, r);
+                }
+            }
+            first = warp_min(first);
+            last = warp_max(last);
+            if (last < 0) {
+                fail = WSTR_READ_NO_REPEAT_STATE;
+            } else {
+                start = first;
+                end = last;
+                const int s_state = run_state[start];
+                int fa = 1 << 30;
+                for (int r = lane; r < n_runs; r += 32)
+                    if (run_state[r] == s_state) fa = min(fa, r);
+                ra = warp_min(fa);
+                for (int pass = 0; pass < 2 && !fail; ++pass) {
+                    if (end >= n_runs) {
+                        fail = WSTR_READ_SEGMENT;   // state_transitions[end]
+                        break;
+                    }
+                    const int e_state = run_state[end];
+                    int lb = -1;
+                    for (int r = lane; r < n_runs; r += 32)
+                        if (run_state[r] == e_state) lb = max(lb, r);
+                    rb = warp_max(lb);
+                    ncuts = rb > ra ? rb - ra : 0;
+                    if (pass == 1) break;
+                    const int sis = p.sis;
+                    const int extra = (((ncuts - 1) % sis) + sis) % sis;
+                    if (extra == 0) break;
+                    end = end + (sis - extra);
+                }
+            }
+        }
+        int nb = 0;
+        if (!fail) {
+            nb = (ncuts + p.sis - 1) / p.sis;
+            if (nb == 0) fail = WSTR_READ_SEGMENT;   // bounds[0]
+        }
+        // bounds[n] = run_start[ra + n*sis + 1] - 1; a window is x[b_n-3 : b_{n+1}+3] and needs
+        // at least one full 6-sample stretch (caller.py:336,358-361)
+        if (!fail && nb > 1) {
+            const int b0 = run_start[ra + 1] - 1;
+            const int bpen = run_start[ra + (nb - 2) * p.sis + 1] - 1;
+            if (b0 - 3 < 0 || bpen > T - 3) fail = WSTR_READ_SEGMENT;
+        }
+        if (lane == 0) {
+            MidState st;
+            st.n_runs = n_runs;
+            st.m = m;
+            st.start = start;
+            st.end = end;
+            st.ra = ra;
+            st.nb = nb;
+            p.state[q] = st;
+            if (fail) p.status[rd.read] = fail;
+        }
+        __syncwarp();
+    }
+}
+
+// Kernel B (one thread per read, first pass only): the smoothing spline's accepted first
+// iteration.  Strictly sequential per read, so reads are spread over threads.
+__global__ void __launch_bounds__(128) mid_fit_kernel(const MidParams p) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p.n) return;
+    const MidRead rd = p.reads[q];
+    if (p.status[rd.read] != WSTR_READ_OK) return;
+    const MidState st = p.state[q];
+    const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap);
+    Cubic cu;
+    lsq_cubic(sc.sx, sc.sy, st.m, cu);
+    const double s = (double)st.m, acc = 0.001 * s;
+    const double fpms = cu.fp - s;
+    // fpcurf: accept if |fp-s| < acc or fp < s; otherwise knots would be added
+    if ((!(fabs(fpms) < acc) && !(fpms < 0.0)) || !(cu.fp == cu.fp)) p.status[rd.read] = WSTR_READ_SPLINE_KNOTS;
+    double *o = p.cubic + (size_t)q * 8;
+    o[0] = cu.xb;
+    o[1] = cu.xe;
+    o[2] = cu.c[0];
+    o[3] = cu.c[1];
+    o[4] = cu.c[2];
+    o[5] = cu.c[3];
+    o[6] = cu.fp;
+}
+
+// Kernel C (one warp per read): rescaled signal + bad-repeat mask (first pass), cost, sequence.
+template <bool SECOND>
+__global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(p.queue + 1, 1);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= p.n) break;
+        const MidRead rd = p.reads[q];
+        if (p.status[rd.read] != WSTR_READ_OK) continue;
+        const MidAutomaton A = p.auts[rd.aut];
+        const MidState st = p.state[q];
+        const int T = rd.T;
+        const double *x = p.x + rd.sig_off;
+        const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap);
+        const int32_t *run_start = sc.run_start, *run_state = sc.run_state;
+        const int n_runs = st.n_runs, ra = st.ra, nb = st.nb;
+        int fail = 0;
+
+        if (!SECOND) {
+            Cubic cu;
+            const double *ci = p.cubic + (size_t)q * 8;
+            cu.xb = ci[0];
+            cu.xe = ci[1];
+            cu.c[0] = ci[2];
+            cu.c[1] = ci[3];
+            cu.c[2] = ci[4];
+            cu.c[3] = ci[5];
+            // ---- rescaled signal (caller.py:312) ------------------------------------------------
+            double *out = p.rescaled + rd.sig_off;
+            for (int t = lane; t < T; t += 32) out[t] = splev3(cu, x[t]);
+            // ---- bad-repeat mask (caller.py:336-344, 409-421) -----------------------------------
+            uint32_t *mw = p.maskbits + rd.mask_off;
+            const int nwords = (T + 31) >> 5;
+            for (int w = lane; w < nwords; w += 32) mw[w] = 0u;
+            __syncwarp();
+            for (int n0 = 0; n0 < nb - 1; n0 += 32) {
+                const int n = n0 + lane;
+                if (n < nb - 1) {
+                    const int b_lo = run_start[ra + n * p.sis + 1] - 1;
+                    const int b_hi = run_start[ra + (n + 1) * p.sis + 1] - 1;
+                    const int c1 = min(b_hi, T - 3);
+                    if (count_segments(x, b_lo, c1) >= p.sis + 1) {
+                        for (int w = b_lo >> 5; w <= (b_hi - 1) >> 5; ++w) {
+                            const int lo = max(b_lo, w << 5), hi = min(b_hi, (w + 1) << 5);   // [lo, hi)
+                            if (hi <= lo) continue;
+                            const int cnt = hi - lo;
+                            const uint32_t bits = (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u)) << (lo & 31);
+                            atomicOr(mw + w, bits);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- state-wise cost (caller.py:138-139) and decoded sequence (:178-187) ----------------
+        {
+            const int start = st.start;
+            const int e_clip = min(st.end, n_runs);
+            const int cnt = e_clip > start ? e_clip - start : 0;
+            for (int r = start + lane; r < start + cnt; r += 32)
+                sc.px[r - start] = fabs(sc.sv[r] - A.values[run_state[r]]);
+            __syncwarp();
+            if (lane == 0) {
+                double cost;
+                if (cnt == 0) {
+                    cost = __longlong_as_double(0x7ff8000000000000LL);   // np.mean([]) is nan
+                } else {
+                    const double *cp = sc.px;
+                    cost = pairwise_sum([cp](int i) { return cp[i]; }, 0, cnt) / (double)cnt;
+                }
+                p.cost[rd.read] = cost;
+            }
+            // python: seq[F - offset : -F] over one character per run
+            const int F = A.flank_length;
+            const int offset = A.seq_idx[run_state[0]];
+            int a = F - offset, b = F == 0 ? 0 : n_runs - F;
+            if (a < 0) a = max(n_runs + a, 0);
+            if (a > n_runs) a = n_runs;
+            if (b < 0) b = 0;
+            const int len = b > a ? b - a : 0;
+            if (lane == 0) p.len[rd.read] = len;
+            if (p.seq && rd.seq_off >= 0) {
+                uint8_t *so = p.seq + rd.seq_off;
+                for (int i = lane; i < len; i += 32) {
+                    if (rd.reverse) so[i] = complement(A.last_base[run_state[b - 1 - i]]);
+                    else so[i] = A.last_base[run_state[a + i]];
+                }
+            }
+        }
+        if (fail && lane == 0) p.status[rd.read] = fail;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// p.queue must point at two zeroed counters
+int wstr_launch_midstage(const MidParams &p, bool second, cudaStream_t s) {
+    if (p.n <= 0) return WSTR_OK;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        WSTR_CUDA(cudaGetDevice(&dev));
+        WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int grid = (p.n + 3) / 4;
+    if (grid > sms * 8) grid = sms * 8;
+    if (second) {
+        mid_stats_kernel<true><<<grid, 128, 0, s>>>(p);
+        mid_finish_kernel<true><<<grid, 128, 0, s>>>(p);
+    } else {
+        mid_stats_kernel<false><<<grid, 128, 0, s>>>(p);
+        mid_fit_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
+        mid_finish_kernel<false><<<grid, 128, 0, s>>>(p);
+    }
+    WSTR_CUDA(cudaGetLastError());
+    return WSTR_OK;
+}
+
+int64_t wstr_mid_scratch_bytes(int T, int mv) {
+    const int64_t R = T / (mv > 2 ? mv - 1 : 1) + 16;
+    int64_t b = ((8 * R + 4 + 7) / 8) * 8;   // run_start (R+1) + run_state (R), int32
+    b += 5 * 8 * R;                           // sv, px, py, sx, sy
+    b += R;                                   // good
+    return (b + 255) / 256 * 256;
+}

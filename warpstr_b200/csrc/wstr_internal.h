@@ -55,7 +55,55 @@ struct FillParams {
     int32_t *trace;              // state index per sample, same offsets as the signal
     double *end_cost;            // may be NULL; indexed by ReadMeta.read
     int32_t *status;             // indexed by ReadMeta.read
+    int32_t respect_status;      // skip reads whose status is already an error (second pass)
 };
+
+// ---- mid-stage (midstage.cu) ------------------------------------------------------------------
+struct MidAutomaton {
+    const double *values;        // [S]
+    const int32_t *seq_idx;      // [S]
+    const uint8_t *rep_mask;     // [S]
+    const uint8_t *last_base;    // [S]
+    int32_t flank_length;
+    int32_t pad_;
+};
+
+struct MidRead {
+    int64_t sig_off;     // element offset into signal / trace / rescaled
+    int64_t mask_off;    // word offset into maskbits
+    int64_t ws_off;      // byte offset into the scratch region
+    int64_t seq_off;     // byte offset into the sequence output, -1 = none
+    int32_t T, aut, read, reverse;
+    int32_t run_cap;     // capacity of the run arrays
+    int32_t pad_;
+};
+
+struct MidState {
+    int32_t n_runs, m, start, end, ra, nb;
+};
+
+struct MidParams {
+    const MidAutomaton *auts;
+    const MidRead *reads;
+    int32_t n;
+    int32_t *queue;              // two zeroed counters
+    const double *x;             // the signal this pass aligned
+    const int32_t *trace;
+    double *rescaled;            // first pass: output
+    uint32_t *maskbits;          // first pass: output
+    unsigned char *scratch;
+    MidState *state;             // [n]
+    double *cubic;               // [n][8]
+    int32_t *len;
+    double *cost;
+    uint8_t *seq;                // may be NULL
+    int32_t *status;
+    int32_t mv, sis;
+    double threshold, max_std;
+};
+
+int wstr_launch_midstage(const MidParams &p, bool second, cudaStream_t s);
+int64_t wstr_mid_scratch_bytes(int T, int mv);
 
 struct wstr_automaton {
     DevAutomaton dev;            // pointers into d_blob
@@ -71,6 +119,8 @@ struct wstr_automaton {
 };
 
 int wstr_set_cuda_error(cudaError_t e, const char *where);
+void wstr_prof_begin(int category, cudaStream_t s);
+void wstr_prof_end(cudaStream_t s);
 
 #define WSTR_CUDA(call)                                                   \
     do {                                                                  \
