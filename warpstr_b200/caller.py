@@ -224,6 +224,22 @@ class CallerEngine:
                             o.get('trace1'), o.get('trace2'), o.get('rescaled'))
         return o
 
+    def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True) -> Dict[str, np.ndarray]:
+        """Array-level end-to-end call: (pinned) host signal buffer in, host arrays out --
+        len1 ('orig'), len2 ('results'), cost1, cost2, status and, optionally, the decoded
+        sequence bytes.  This is the call a batch pipeline makes; ``call_batch`` wraps it into
+        ``CallerResult`` objects."""
+        import torch
+        with torch.cuda.device(self.device):
+            d_sig = host_signal.to(self.device, non_blocking=True)
+            o = self.call_packed(d_sig, off, lengths, aut, rev, want_seq=want_seq)
+            out = {k: o[k].cpu().numpy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+            if want_seq:
+                out['seq1'] = o['seq1'].cpu().numpy()
+                out['seq2'] = o['seq2'].cpu().numpy()
+                out['seq_off'] = o['seq_off']
+        return out
+
     def results_from(self, o, signals, aut_ids, reverse) -> List[CallerResult]:
         """Device results -> CallerResult list; reads the device could not finish (status != 0)
         are redone on the host path or raise what the reference raises."""

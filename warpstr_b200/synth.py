@@ -142,3 +142,60 @@ def to_raw_int16(rng: np.random.Generator, norm: np.ndarray, pad: int = 8192,
     spikes = rng.random(raw.shape[0]) < spike_rate
     raw[spikes] = np.where(rng.random(int(spikes.sum())) < 0.5, 1500, 100)
     return raw.astype(np.int16), left, left + len(norm) - 1
+
+
+def make_read_batch(locus: SynthLocus, n: int, seed: int = 0, noise: float = 0.15,
+                    reverse_fraction: float = 0.5, pm: Optional[PoreModel] = None,
+                    dwell: Tuple[int, int] = (5, 13)):
+    """Vectorised generator for large batches: same model as :func:`make_reads`, different
+    random stream.  Returns (signal f64 concatenated with even starts, offsets i64[n],
+    lengths i32[n], reverse u8[n], truth_len i32[n])."""
+    pm = pm or get_pore_model()
+    rng = np.random.default_rng([seed, 0xBA7C4])
+    k = pm.kmersize
+    seqs, rev, truth = [], np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32)
+    rflags = rng.random(n) < reverse_fraction
+    for i in range(n):
+        allele = draw_allele(rng, locus.units)
+        s = locus.left + allele + locus.right
+        if rflags[i]:
+            s = reverse_complement(s)
+            rev[i] = 1
+        truth[i] = len(allele)
+        seqs.append(s)
+    nb = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
+    codes = np.frombuffer(''.join(seqs).encode('ascii'), dtype=np.uint8)
+    lut = np.zeros(256, dtype=np.int64)
+    for i, b in enumerate('ACGT'):
+        lut[ord(b)] = i
+    c = lut[codes]
+    idx = np.zeros(len(c) - k + 1, dtype=np.int64)
+    for p in range(k):
+        idx = idx * 4 + c[p:len(c) - k + 1 + p]
+    # drop the k-mers that straddle two reads
+    starts = np.concatenate(([0], np.cumsum(nb)[:-1]))
+    keep = np.ones(len(idx), dtype=bool)
+    for p in range(1, k):
+        bad = starts[1:] - p
+        keep[bad[bad >= 0]] = False
+    levels = pm.table[idx[keep]]
+    nk = nb - k + 1                                   # k-mers per read
+    dw = rng.integers(dwell[0], dwell[1] + 1, size=len(levels))
+    kstart = np.concatenate(([0], np.cumsum(nk)))
+    cum = np.concatenate(([0], np.cumsum(dw)))
+    lengths = (cum[kstart[1:]] - cum[kstart[:-1]]).astype(np.int32)
+    sig = np.repeat(levels, dw)
+    sig += rng.normal(0.0, noise, size=sig.shape[0])
+    # re-pack with even starts (the kernels want 16-byte aligned reads)
+    padded = (lengths.astype(np.int64) + 1) & ~1
+    offsets = np.zeros(n, dtype=np.int64)
+    offsets[1:] = np.cumsum(padded[:-1])
+    if (lengths & 1).any():
+        out = np.zeros(int(padded.sum()) + 2, dtype=np.float64)
+        src = np.concatenate(([0], np.cumsum(lengths.astype(np.int64))))
+        shift = offsets - src[:-1]
+        dst_idx = np.arange(sig.shape[0], dtype=np.int64) + np.repeat(shift, lengths)
+        out[dst_idx] = sig
+    else:
+        out = np.concatenate((sig, np.zeros(2)))
+    return out, offsets, lengths, rev, truth
