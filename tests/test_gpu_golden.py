@@ -1,0 +1,104 @@
+"""GPU: the CUDA path against the committed reference goldens (tests/golden/, made from the
+unmodified reference by oracle/make_golden.py) -- the whole call, the normalisation kernel
+and the pore-model lookup, all through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from warpstr_b200.automata import StateAutomata
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def test_whole_call_matches_reference_goldens(built_lib):
+    from warpstr_b200.caller import CallerEngine
+    z = np.load(os.path.join(GOLD, 'caller.npz'))
+    cases = json.loads(str(z['cases']))
+    by_flank = {}
+    for c in cases:
+        by_flank.setdefault(c['flank'], []).append(c)
+    for flank, group in by_flank.items():
+        eng = CallerEngine()
+        ids = {}
+        sigs, aut, rev = [], [], []
+        for c in group:
+            rx = c['reverse_regex'] if c['reverse'] else c['template_regex']
+            if rx not in ids:
+                ids[rx] = eng.add_automaton(StateAutomata(rx), flank)
+            sigs.append(z[f"{c['key']}_signal"]); aut.append(ids[rx]); rev.append(c['reverse'])
+        packed = eng.upload(sigs, aut, rev)
+        o = eng.call_packed(*packed, want_debug=True)
+        assert not o['status'].cpu().numpy().any()
+        t1, t2, resc = (o[k].cpu().numpy() for k in ('trace1', 'trace2', 'rescaled'))
+        res = eng.results_from(o, sigs, aut, rev)
+        for n, c in enumerate(group):
+            k = c['key']
+            a, ln = int(packed[1][n]), int(packed[2][n])
+            assert np.array_equal(t1[a:a + ln], z[f'{k}_ref_trace1']), k
+            assert np.array_equal(resc[a:a + ln], z[f'{k}_ref_rescaled']), k
+            assert np.array_equal(t2[a:a + ln], z[f'{k}_ref_trace2']), k
+            assert res[n].seq == c['seq'] and res[n].resc_seq == c['resc_seq'], k
+            assert len(res[n].resc_seq) == c['truth_len'], k
+            # float tolerance of the north star: 1e-6 relative; in fact bit-equal
+            assert res[n].cost == pytest.approx(c['cost'], rel=1e-6) and res[n].cost == c['cost'], k
+            assert res[n].resc_cost == c['resc_cost'], k
+
+
+@pytest.mark.parametrize('mode', ['Brute', 'None', 'median3', 'median5'])
+def test_normalisation_kernel_matches_reference_goldens(built_lib, mode):
+    from warpstr_b200.normalize import normalize_windows
+    z = np.load(os.path.join(GOLD, 'normalize.npz'))
+    cases = json.loads(str(z['cases']))
+    key = {'Brute': 'brute', 'None': 'none', 'median3': 'median3', 'median5': 'median5'}[mode]
+    use = [c for c in cases if f"{c['key']}_ref_norm_{key}" in z]
+    raws = [z[f"{c['key']}_raw"] for c in use]
+    wins = [(c['lo'], c['hi']) for c in use]
+    got = normalize_windows(raws, wins, mode)
+    for c, g in zip(use, got):
+        want = z[f"{c['key']}_ref_norm_{key}"]
+        assert g.shape == want.shape, c['key']
+        assert np.array_equal(g, want, equal_nan=True), (c['key'], mode)
+
+
+def test_normalisation_window_clipping_and_many_reads(built_lib):
+    from oracle import normalize_oracle as no
+    from warpstr_b200.normalize import get_data_processed, normalize_windows
+    rng = np.random.default_rng(8)
+    raws = [rng.integers(250, 1000, size=int(n)).astype(np.int16) for n in rng.integers(3000, 9000, size=400)]
+    for r in raws[::7]:
+        r[rng.integers(0, len(r), 5)] = 1700
+    wins = [(int(rng.integers(0, len(r) - 10)), int(rng.integers(0, 2 * len(r)))) for r in raws]
+    got = normalize_windows(raws, wins, 'Brute')
+    for r, w, g in zip(raws, wins, got):
+        assert np.array_equal(g, no.get_data_processed(r, w, 'Brute'))
+    assert np.array_equal(get_data_processed(raws[0]), no.get_data_processed(raws[0], (0, len(raws[0]) - 1)))
+
+
+def test_pore_lookup_matches_reference_golden(built_lib):
+    from warpstr_b200.pore_model import get_pore_model
+    sq = np.load(os.path.join(GOLD, 'squiggle.npz'))
+    pm = get_pore_model()
+    assert np.array_equal(pm.generate_signal(str(sq['seq'])), sq['ref_signal'])
+    assert pm.generate_signal('ACG').shape == (0,)
+    with pytest.raises(IndexError):
+        pm.generate_signal('ACGTNACGTAC')
+
+
+def test_engine_raises_reference_exception_types(built_lib):
+    """A read the reference would abort on is reported with the reference's exception type."""
+    from warpstr_b200 import synth
+    from warpstr_b200.caller import CallerEngine
+    locus = synth.make_locus('AAAT', seed=2)
+    eng = CallerEngine()
+    a = eng.add_automaton(StateAutomata(locus.template_regex), 110)
+    rd = [r for r in synth.make_reads(locus, 4, seed=3) if not r.reverse][0]
+    with pytest.raises(TypeError):       # never reaches the repeat: splrep has < 4 points
+        eng.call_batch([rd.signal[:300]], [a], [False])
+    with pytest.raises(IndexError):      # T <= min_values_per_state
+        eng.call_batch([rd.signal[:3]], [a], [False])
+    ok = eng.call_batch([rd.signal[:300], rd.signal], [a, a], [False, False], engine='gpu') \
+        if False else eng.call_batch([rd.signal], [a], [False])
+    assert len(ok[0].resc_seq) == rd.truth_len

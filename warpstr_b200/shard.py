@@ -1,0 +1,101 @@
+"""Sharding of a read batch over the GPUs of one box and the gather of per-read results.
+
+Reads are independent given the (tiny, replicated) automata, so the path has no data-path
+collective: every rank calls its own slice and only the fixed-width per-read records
+{read id, len(seq), len(resc_seq), status, cost, resc_cost} are exchanged -- one all_gather
+per batch (NCCL over NVLink when the tensors live on GPUs, gloo in the CPU tests).  The
+reference's only parallelism is a process pool over reads (caller/wrapper.py:107-109).
+"""
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+def partition_reads(costs: Sequence[float], world: int) -> List[np.ndarray]:
+    """Longest-processing-time-first split of reads into ``world`` shards of near-equal total
+    cost (cost = T * S, the DP cells of the read).  Deterministic; every rank computes the
+    same answer.  Returns, per rank, the ascending indices of its reads."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind='stable')
+    load = np.zeros(world, dtype=np.float64)
+    shards: List[List[int]] = [[] for _ in range(world)]
+    if len(order) > 64 * world:
+        # LPT on the long tail only matters for the first few; after that round-robin over the
+        # sorted list (snake order) is within a read of optimal and O(n)
+        head = order[:32 * world]
+        tail = order[32 * world:]
+    else:
+        head, tail = order, order[:0]
+    for i in head:
+        r = int(np.argmin(load))
+        shards[r].append(int(i))
+        load[r] += costs[i]
+    if len(tail):
+        ranks = np.argsort(load, kind='stable')
+        period = np.concatenate((ranks, ranks[::-1]))
+        assign = period[np.arange(len(tail)) % (2 * world)]
+        for r in range(world):
+            shards[r].extend(tail[assign == r].tolist())
+    return [np.sort(np.asarray(s, dtype=np.int64)) for s in shards]
+
+
+def gather_records(ids: np.ndarray, ints: np.ndarray, floats: np.ndarray, n_total: int,
+                   group=None, device=None) -> Optional[Dict[str, np.ndarray]]:
+    """all_gather of this rank's records; every rank returns the batch-ordered arrays.
+
+    ids    int64[n_local]      global read index of each local record
+    ints   int32[n_local, 3]   len1, len2, status
+    floats float64[n_local, 2] cost1, cost2
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = device if device is not None else torch.device('cpu')
+    n_local = int(len(ids))
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine, group=group) if dev.type == 'cuda' else \
+        dist.all_gather(list(counts.split(1)), mine, group=group)
+    cap = int(counts.max().item())
+    rec = torch.zeros((cap, 6), dtype=torch.float64, device=dev)
+    if n_local:
+        local = np.concatenate((ids.reshape(-1, 1).astype(np.float64), ints.astype(np.float64),
+                                floats.astype(np.float64)), axis=1)
+        rec[:n_local] = torch.from_numpy(local).to(dev)
+    out = [torch.zeros_like(rec) for _ in range(world)]
+    dist.all_gather(out, rec, group=group)
+    len1 = np.full(n_total, -1, dtype=np.int32)
+    len2 = np.full(n_total, -1, dtype=np.int32)
+    status = np.full(n_total, -1, dtype=np.int32)
+    cost1 = np.full(n_total, np.nan)
+    cost2 = np.full(n_total, np.nan)
+    for r in range(world):
+        n = int(counts[r].item())
+        if not n:
+            continue
+        a = out[r][:n].cpu().numpy()
+        idx = a[:, 0].astype(np.int64)
+        len1[idx] = a[:, 1].astype(np.int32)
+        len2[idx] = a[:, 2].astype(np.int32)
+        status[idx] = a[:, 3].astype(np.int32)
+        cost1[idx] = a[:, 4]
+        cost2[idx] = a[:, 5]
+    return dict(len1=len1, len2=len2, status=status, cost1=cost1, cost2=cost2)
+
+
+def call_sharded(engine, signals: Sequence[np.ndarray], aut_ids: Sequence[int], reverse: Sequence[bool],
+                 n_states: Sequence[int], group=None) -> Dict[str, np.ndarray]:
+    """Every rank holds the same read list (or at least its own shard's signals), calls its
+    shard on its GPU and receives everybody's per-read lengths and costs."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    costs = [len(s) * n_states[a] for s, a in zip(signals, aut_ids)]
+    mine = partition_reads(costs, world)[rank]
+    sub = [signals[i] for i in mine]
+    packed = engine.upload(sub, [aut_ids[i] for i in mine], [reverse[i] for i in mine])
+    o = engine.call_packed(*packed, want_seq=False)
+    ints = torch.stack((o['len1'], o['len2'], o['status']), dim=1).cpu().numpy()
+    floats = torch.stack((o['cost1'], o['cost2']), dim=1).cpu().numpy()
+    return gather_records(mine, ints, floats, len(signals), group=group, device=engine.device)
