@@ -99,6 +99,5 @@ def test_engine_raises_reference_exception_types(built_lib):
         eng.call_batch([rd.signal[:300]], [a], [False])
     with pytest.raises(IndexError):      # T <= min_values_per_state
         eng.call_batch([rd.signal[:3]], [a], [False])
-    ok = eng.call_batch([rd.signal[:300], rd.signal], [a, a], [False, False], engine='gpu') \
-        if False else eng.call_batch([rd.signal], [a], [False])
+    ok = eng.call_batch([rd.signal], [a], [False])
     assert len(ok[0].resc_seq) == rd.truth_len

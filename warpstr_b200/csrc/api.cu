@@ -676,7 +676,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     const bool own_resc = out->d_rescaled == nullptr;
     const bool own_trace = out->d_trace1 == nullptr || out->d_trace2 == nullptr;
     const CallPlan c = plan_call(n_automata, n_reads, sig_off, lengths, mv, own_resc, own_trace);
-    if ((int64_t)c.o_warp + (1 << 16) > workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    if ((int64_t)c.o_warp >= workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
     unsigned char *ws = static_cast<unsigned char *>(d_workspace);
     int32_t *d_queue = reinterpret_cast<int32_t *>(ws + c.o_queue);
     MidAutomaton *d_mauts = reinterpret_cast<MidAutomaton *>(ws + c.o_mauts);
