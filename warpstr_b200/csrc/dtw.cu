@@ -223,15 +223,15 @@ __device__ __forceinline__ void dp_row_single(LaneState<KC + KG, MV> &s, const L
     }
 }
 
-// rows [i0, i1) with one (SHORT, BAND) setting
+// rows [i0, i1) of the tile starting at row `tile0`, one (SHORT, BAND) setting
 template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
 __device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
-                                           const double *__restrict__ xs, int i0, const int i1,
+                                           const double *__restrict__ xs, const int tile0, int i0, const int i1,
                                            double *__restrict__ Qlane, const double *__restrict__ Qbase,
                                            uint32_t *__restrict__ dir_lane) {
     constexpr int W = (KC + KG + 7) / 8;
     constexpr int CY = MV - 1;
-    const double *xp = xs + (i0 & (CH - 1));
+    const double *xp = xs + (i0 - tile0);
     uint32_t *dp = dir_lane + static_cast<int64_t>(i0) * (W * 32);
 #pragma unroll 1
     for (; i0 + CY <= i1; i0 += CY) {
@@ -247,38 +247,41 @@ __device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const Lane
     }
 }
 
-// rows [i0, i1) of one signal tile (all inside one band setting); mask words pick SHORT rows
+// first row in (a, limit] whose mask bit differs from row a's (or limit)
+__device__ __forceinline__ int mask_run_end(const uint32_t *__restrict__ mw, int a, const int limit, uint32_t &bit) {
+    uint32_t word = __ldg(mw + (a >> 5));
+    bit = (word >> (a & 31)) & 1u;
+    uint32_t diff = (bit ? ~word : word) >> (a & 31);
+    int b = a;
+    for (;;) {
+        if (diff) {
+            b += __ffs(diff) - 1;
+            break;
+        }
+        b = (b | 31) + 1;                // next word
+        if (b >= limit) break;
+        word = __ldg(mw + (b >> 5));
+        diff = bit ? ~word : word;
+    }
+    return b < limit ? b : limit;
+}
+
+// rows [i0, i1) of one signal tile (all inside one band setting); mask bits pick SHORT rows
 template <int KC, int KG, int DEG, int MV, bool BAND>
 __device__ __forceinline__ void dp_tile_rows(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
-                                             const double *__restrict__ xs, int i0, const int i1,
+                                             const double *__restrict__ xs, const int tile0, int i0, const int i1,
                                              const uint32_t *__restrict__ mw_ptr, double *__restrict__ Qlane,
                                              const double *__restrict__ Qbase, uint32_t *__restrict__ dir_lane) {
     if (!mw_ptr) {
-        dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, i0, i1, Qlane, Qbase, dir_lane);
+        dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, i1, Qlane, Qbase, dir_lane);
         return;
     }
     while (i0 < i1) {
-        const int blk_end = min(i1, (i0 | 31) + 1);
-        const uint32_t word = __ldg(mw_ptr + (i0 >> 5));
-        const int n = blk_end - i0;
-        const uint32_t span = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << (i0 & 31);
-        const uint32_t bits = word & span;
-        if (bits == 0u) {
-            dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, i0, blk_end, Qlane, Qbase, dir_lane);
-        } else if (bits == span) {
-            dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, i0, blk_end, Qlane, Qbase, dir_lane);
-        } else {   // mixed block: maximal runs of equal bits
-            int a = i0;
-            while (a < blk_end) {
-                const uint32_t bit = (word >> (a & 31)) & 1u;
-                int b = a + 1;
-                while (b < blk_end && ((word >> (b & 31)) & 1u) == bit) ++b;
-                if (bit) dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, a, b, Qlane, Qbase, dir_lane);
-                else dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, a, b, Qlane, Qbase, dir_lane);
-                a = b;
-            }
-        }
-        i0 = blk_end;
+        uint32_t bit;
+        const int b = mask_run_end(mw_ptr, i0, i1, bit);
+        if (bit) dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, tile0, i0, b, Qlane, Qbase, dir_lane);
+        else dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, b, Qlane, Qbase, dir_lane);
+        i0 = b;
     }
 }
 
@@ -479,9 +482,11 @@ dtw_fill_kernel(const FillParams p) {
             const int i_end = min(T, (c + 1) * CH);
             const int i_mid = min(max(band_start, i_begin), i_end);   // rows from here on are banded
             if (i_begin < i_mid)
-                dp_tile_rows<KC, KG, DEG, MV, false>(s, lc, xs, i_begin, i_mid, mw_ptr, Qlane, Qbase, dir_lane);
+                dp_tile_rows<KC, KG, DEG, MV, false>(s, lc, xs, c * CH, i_begin, i_mid, mw_ptr, Qlane, Qbase,
+                                                     dir_lane);
             if (i_mid < i_end)
-                dp_tile_rows<KC, KG, DEG, MV, true>(s, lc, xs, i_mid, i_end, mw_ptr, Qlane, Qbase, dir_lane);
+                dp_tile_rows<KC, KG, DEG, MV, true>(s, lc, xs, c * CH, i_mid, i_end, mw_ptr, Qlane, Qbase,
+                                                    dir_lane);
             __syncwarp();                          // every lane is done with this tile
             if (c + 2 < nchunks) issue(c + 2);     // refill it
         }

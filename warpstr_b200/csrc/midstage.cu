@@ -32,34 +32,67 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- numpy pairwise summation over f(0..n-1) ---------------------------------------------------
+// (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE).  The recursion of the original
+// (halves, the left one rounded down to a multiple of 8) is unrolled onto an explicit stack so
+// that the kernels have a static frame size.
 template <class F>
-__device__ double pairwise_sum(const F &f, int start, int n) {
+__device__ __forceinline__ double pairwise_leaf(const F &f, int start, int n) {
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res += f(start + i);
         return res;
     }
-    if (n <= 128) {
-        double r0 = f(start), r1 = f(start + 1), r2 = f(start + 2), r3 = f(start + 3), r4 = f(start + 4),
-               r5 = f(start + 5), r6 = f(start + 6), r7 = f(start + 7);
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
-            r0 += f(start + i);
-            r1 += f(start + i + 1);
-            r2 += f(start + i + 2);
-            r3 += f(start + i + 3);
-            r4 += f(start + i + 4);
-            r5 += f(start + i + 5);
-            r6 += f(start + i + 6);
-            r7 += f(start + i + 7);
-        }
-        double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-        for (; i < n; ++i) res += f(start + i);
-        return res;
+    double r0 = f(start), r1 = f(start + 1), r2 = f(start + 2), r3 = f(start + 3), r4 = f(start + 4),
+           r5 = f(start + 5), r6 = f(start + 6), r7 = f(start + 7);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 += f(start + i);
+        r1 += f(start + i + 1);
+        r2 += f(start + i + 2);
+        r3 += f(start + i + 3);
+        r4 += f(start + i + 4);
+        r5 += f(start + i + 5);
+        r6 += f(start + i + 6);
+        r7 += f(start + i + 7);
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return pairwise_sum(f, start, n2) + pairwise_sum(f, start + n2, n - n2);
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += f(start + i);
+    return res;
+}
+
+template <class F>
+__device__ double pairwise_sum(const F &f, int start0, int n0) {
+    if (n0 <= 128) return pairwise_leaf(f, start0, n0);
+    struct Frame {
+        int start, n, stage;
+        double left;
+    };
+    Frame st[28];
+    int sp = 0;
+    st[sp++] = Frame{start0, n0, 0, 0.0};
+    double ret = 0.0;
+    while (sp > 0) {
+        Frame &fr = st[sp - 1];
+        if (fr.n <= 128) {
+            ret = pairwise_leaf(f, fr.start, fr.n);
+            --sp;
+            continue;
+        }
+        int n2 = fr.n / 2;
+        n2 -= n2 % 8;
+        if (fr.stage == 0) {
+            fr.stage = 1;
+            st[sp++] = Frame{fr.start, n2, 0, 0.0};
+        } else if (fr.stage == 1) {
+            fr.left = ret;
+            fr.stage = 2;
+            st[sp++] = Frame{fr.start + n2, fr.n - n2, 0, 0.0};
+        } else {
+            ret = fr.left + ret;
+            --sp;
+        }
+    }
+    return ret;
 }
 
 // ---- FITPACK pieces for the single-interval cubic ------------------------------------------------
