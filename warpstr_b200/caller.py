@@ -97,6 +97,8 @@ class CallerEngine:
         self.automata: List[_lib.DeviceAutomaton] = []
         self.tables: List[dict] = []
         self._ws = None
+        self._copy_stream = None
+        self._host_out = None
 
     # -- automata ------------------------------------------------------------------------
     def add_automaton(self, sta, flank_length: int) -> int:
@@ -224,21 +226,82 @@ class CallerEngine:
                             o.get('trace1'), o.get('trace2'), o.get('rescaled'))
         return o
 
-    def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True) -> Dict[str, np.ndarray]:
+    def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True,
+                    chunk_reads: int = 25000) -> Dict[str, np.ndarray]:
         """Array-level end-to-end call: (pinned) host signal buffer in, host arrays out --
         len1 ('orig'), len2 ('results'), cost1, cost2, status and, optionally, the decoded
-        sequence bytes.  This is the call a batch pipeline makes; ``call_batch`` wraps it into
-        ``CallerResult`` objects."""
+        sequence bytes.  The batch is cut into chunks of ``chunk_reads`` reads; a copy stream
+        moves chunk i+1 to the device and chunk i-1's results back while the compute stream
+        works on chunk i.  ``call_batch`` wraps this into ``CallerResult`` objects."""
         import torch
+        n = len(lengths)
+        lengths = np.asarray(lengths, dtype=np.int32)
+        off = np.asarray(off, dtype=np.int64)
+        aut = np.asarray(aut, dtype=np.int32)
+        rev = np.asarray(rev, dtype=np.uint8)
+        bounds = list(range(0, n, max(1, chunk_reads))) + [n]
+        cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
+        seq_off = np.zeros(n + 1, dtype=np.int64)
+        seq_off[1:] = np.cumsum(cap)
+        out = self._host_results(n, int(seq_off[-1]) if want_seq else 0)
         with torch.cuda.device(self.device):
-            d_sig = host_signal.to(self.device, non_blocking=True)
-            o = self.call_packed(d_sig, off, lengths, aut, rev, want_seq=want_seq)
-            out = {k: o[k].cpu().numpy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
-            if want_seq:
-                out['seq1'] = o['seq1'].cpu().numpy()
-                out['seq2'] = o['seq2'].cpu().numpy()
-                out['seq_off'] = o['seq_off']
-        return out
+            comp = torch.cuda.current_stream()
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            cs = self._copy_stream
+            total = int(off[-1] + ((int(lengths[-1]) + 1) & ~1) + 2) if n else 0
+            d_sig = torch.empty(min(total, host_signal.numel()), dtype=torch.float64, device=self.device)
+            cs.wait_stream(comp)
+            ready = []
+            for a, b in zip(bounds[:-1], bounds[1:]):          # all H2D copies, in order, on the copy stream
+                lo = int(off[a])
+                hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel())
+                with torch.cuda.stream(cs):
+                    d_sig[lo:hi].copy_(host_signal[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                ready.append((lo, hi, ev))
+            keep = []
+            for (a, b), (lo, hi, ev) in zip(zip(bounds[:-1], bounds[1:]), ready):
+                comp.wait_event(ev)
+                o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b], want_seq=want_seq)
+                done = torch.cuda.Event()
+                done.record(comp)
+                with torch.cuda.stream(cs):                     # results back while the next chunk computes
+                    cs.wait_event(done)
+                    for k in ('len1', 'len2', 'cost1', 'cost2', 'status'):
+                        out[k][a:b].copy_(o[k], non_blocking=True)
+                    if want_seq:
+                        s0, s1 = int(seq_off[a]), int(seq_off[b])
+                        out['seq1'][s0:s1].copy_(o['seq1'][:s1 - s0], non_blocking=True)
+                        out['seq2'][s0:s1].copy_(o['seq2'][:s1 - s0], non_blocking=True)
+                keep.append(o)
+            cs.synchronize()
+            comp.wait_stream(cs)
+        res = {k: out[k][:n].numpy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+        if want_seq:
+            res['seq1'] = out['seq1'][:int(seq_off[-1])].numpy()
+            res['seq2'] = out['seq2'][:int(seq_off[-1])].numpy()
+            res['seq_off'] = seq_off[:-1]
+        return res
+
+    def _host_results(self, n: int, seq_bytes: int):
+        """Pinned host buffers for the per-read results, grown on demand and reused."""
+        import torch
+        cur = self._host_out
+        if cur is None or cur['len1'].numel() < n or cur['seq1'].numel() < seq_bytes:
+            n_cap = max(n, cur['len1'].numel() if cur else 0)
+            s_cap = max(seq_bytes, cur['seq1'].numel() if cur else 0, 1)
+            pin = torch.cuda.is_available()
+            cur = dict(len1=torch.empty(n_cap, dtype=torch.int32, pin_memory=pin),
+                       len2=torch.empty(n_cap, dtype=torch.int32, pin_memory=pin),
+                       cost1=torch.empty(n_cap, dtype=torch.float64, pin_memory=pin),
+                       cost2=torch.empty(n_cap, dtype=torch.float64, pin_memory=pin),
+                       status=torch.empty(n_cap, dtype=torch.int32, pin_memory=pin),
+                       seq1=torch.empty(s_cap, dtype=torch.uint8, pin_memory=pin),
+                       seq2=torch.empty(s_cap, dtype=torch.uint8, pin_memory=pin))
+            self._host_out = cur
+        return cur
 
     def results_from(self, o, signals, aut_ids, reverse) -> List[CallerResult]:
         """Device results -> CallerResult list; reads the device could not finish (status != 0)
