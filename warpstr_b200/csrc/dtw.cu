@@ -115,6 +115,20 @@ struct LaneConsts {
 template <int KG>
 __host__ __device__ constexpr int q_row_len() { return 32 * KG + 40; }
 
+// best = min(best, cand) with the reference's strict '<'; when cand wins, OR `bit` into codes.
+// Per cell the 4-bit code is a mask of the candidates that took the lead in turn (bit r =
+// incoming edge r); candidates are tried in list order, so the winner is the highest set bit.
+__device__ __forceinline__ void take_min(double &best, uint32_t &codes, const double cand, const uint32_t bit) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.lt.f64 p, %2, %0;\n"
+        "@p mov.f64 %0, %2;\n"
+        "@p or.b32 %1, %1, %3;\n"
+        "}\n"
+        : "+d"(best), "+r"(codes)
+        : "d"(cand), "r"(bit));
+}
+
 // One DP row at pipeline phase PH (leaves the state at phase PH+1).
 // SHORT: this row allows dwell mv-1 (masked row of the second pass).
 // BAND: the end band is active (caller.py:223-224).
@@ -144,20 +158,17 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
         const double ae = fabs(x - s.v[k]);
         const double qhere = offer<K, MV, SHORT, PH>(s, k);
         const double stay = s.D[k] + ae;
-        const double ch = qprev + ae;
-        const bool take = ch < stay;
-        double best = take ? ch : stay;
-        uint32_t code = take ? 1u : 0u;
+        double best = stay;
+        take_min(best, codes[k >> 3], qprev + ae, 1u << (4 * (k & 7)));
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
                 best = INF;
-                code = 0u;
+                codes[k >> 3] &= ~(0xfu << (4 * (k & 7)));
             }
         }
         advance<K, MV, PH>(s, k, ae, stay);
         s.D[k] = best;
         qprev = qhere;
-        codes[k >> 3] |= code << (4 * (k & 7));
     }
 
     // ---- generic slots: stay, then up to DEG incoming edges in list order --------------------
@@ -167,42 +178,37 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
         const double ae = fabs(x - s.v[k]);
         const double stay = s.D[k] + ae;
         double best = stay;
-        uint32_t code = 0u;
 #pragma unroll
         for (int r = 0; r < DEG; ++r) {
             const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
-            const double c = Qrow[idx] + ae;
-            if (c < best) {
-                best = c;
-                code = static_cast<uint32_t>(r + 1);
-            }
+            take_min(best, codes[k >> 3], Qrow[idx] + ae, 1u << (4 * (k & 7) + r));
         }
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
                 best = INF;
-                code = 0u;
+                codes[k >> 3] &= ~(0xfu << (4 * (k & 7)));
             }
         }
         advance<K, MV, PH>(s, k, ae, stay);
         s.D[k] = best;
-        codes[k >> 3] |= code << (4 * (k & 7));
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) dir_lane[w * 32] = codes[w];
 }
 
-// mv-1 consecutive rows: every role returns to its register, nothing has to be moved
+// mv-1 consecutive rows: every role returns to its register, nothing has to be moved.
+// xv holds the rows' samples (fetched one cycle ahead by the caller).
 template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, int PH = 0>
 __device__ __forceinline__ void dp_rows_cycle(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
-                                              const double *__restrict__ xs, double *__restrict__ Qlane,
+                                              const double (&xv)[MV - 1], double *__restrict__ Qlane,
                                               const double *__restrict__ Qbase,
                                               uint32_t *__restrict__ dir_lane) {
     constexpr int W = (KC + KG + 7) / 8;
     constexpr int QL = q_row_len<KG>();
-    dp_row<KC, KG, DEG, MV, SHORT, BAND, PH>(s, lc, xs[PH], Qlane + PH * QL, Qbase + PH * QL,
+    dp_row<KC, KG, DEG, MV, SHORT, BAND, PH>(s, lc, xv[PH], Qlane + PH * QL, Qbase + PH * QL,
                                             dir_lane + PH * (W * 32));
     if constexpr (PH + 1 < MV - 1)
-        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, PH + 1>(s, lc, xs, Qlane, Qbase, dir_lane);
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, PH + 1>(s, lc, xv, Qlane, Qbase, dir_lane);
 }
 
 // a single row from phase 0 back to phase 0 (registers rotated by hand; used for the few rows
@@ -233,9 +239,17 @@ __device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const Lane
     constexpr int CY = MV - 1;
     const double *xp = xs + (i0 - tile0);
     uint32_t *dp = dir_lane + static_cast<int64_t>(i0) * (W * 32);
+    double xv[CY], xn[CY];
+#pragma unroll
+    for (int j = 0; j < CY; ++j) xn[j] = xp[j];          // may run a few samples past the tile: unused then
 #pragma unroll 1
     for (; i0 + CY <= i1; i0 += CY) {
-        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND>(s, lc, xp, Qlane, Qbase, dp);
+#pragma unroll
+        for (int j = 0; j < CY; ++j) {
+            xv[j] = xn[j];
+            xn[j] = xp[CY + j];                          // next cycle's samples, ahead of the barriers
+        }
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND>(s, lc, xv, Qlane, Qbase, dp);
         xp += CY;
         dp += CY * (W * 32);
     }
@@ -323,7 +337,8 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
         int t = 0;
         while (t < 32 && i - t > 0) {
             const uint32_t wt = __shfl_sync(FULL, w, t);
-            const uint32_t code = (wt >> (4 * (u & 7))) & 15u;
+            const uint32_t nib = (wt >> (4 * (u & 7))) & 15u;
+            const uint32_t code = 32u - static_cast<uint32_t>(__clz(nib));   // last candidate that took the lead
             if (lane == t) my = st;
             if (code == 0u) {
                 t += 1;
@@ -358,7 +373,7 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
 // per-warp shared memory: [sig 2 x CH f64][published rows 2 x q_row_len f64][2 mbarriers]
 template <int KG, int MV>
 struct alignas(16) FillSmem {
-    double sig[2][CH];
+    double sig[2][CH];                   // look-ahead reads may run up to 2*(mv-1) samples past a tile (into Q: unused)
     double Q[MV - 1][q_row_len<KG>()];   // one published buffer per pipeline phase
     uint64_t bar[2];
 };
@@ -366,9 +381,14 @@ struct alignas(16) FillSmem {
 #ifndef WSTR_K8_BLOCKS
 #define WSTR_K8_BLOCKS 4
 #endif
+#ifdef WSTR_MAXNREG
+#define WSTR_FILL_BOUNDS __maxnreg__(WSTR_MAXNREG)
+#else
+#define WSTR_FILL_BOUNDS \
+    __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 8 ? WSTR_K8_BLOCKS : (KC + KG <= 12 ? 3 : 2)))
+#endif
 template <int KC, int KG, int DEG, int MV>
-__global__ void __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 8 ? WSTR_K8_BLOCKS : (KC + KG <= 12 ? 3 : 2)))
-dtw_fill_kernel(const FillParams p) {
+__global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int K = KC + KG;
     constexpr int W = (K + 7) / 8;

@@ -8,7 +8,9 @@
 #define WSTR_MAX_K 16            // states per lane in the widest kernel (32*16 = 512 positions)
 #define WSTR_MAX_MV 8
 #define WSTR_SIG_CHUNK 126       // samples per bulk-copied signal tile (1008 B; a multiple of the 3-row cycle)
+#ifndef WSTR_WARPS_PER_CTA
 #define WSTR_WARPS_PER_CTA 4
+#endif
 #define WSTR_MAX_DEG 4           // incoming edges of a generic-slot state
 #define WSTR_LANE_TAB_STRIDE 8   // u32 per lane: band bits, slot-0 source, gsrc[0..5]
 #define WSTR_PRED_STRIDE 8       // i16 per position: predecessor position by direction code
