@@ -304,7 +304,8 @@ def main():
         tpath = os.path.join(ROOT, 'profiles', 'fill_traffic.json')
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get('dram_bytes_per_launch_at_bench_size')
+                tj = json.load(open(tpath))
+                traffic = tj.get('dram_bytes_per_launch_at_bench_size') * (args.reads / waves) / tj.get('reads', 100000)
             except Exception:
                 traffic = None
         line = {

@@ -1,0 +1,74 @@
+"""GPU: configuration knobs of the hot path (tr_calling_config.*, rescaling.*) against the
+oracle, and the per-read status / host-evaluation paths."""
+import numpy as np
+import pytest
+
+from oracle import caller_oracle as co
+from warpstr_b200 import synth
+from warpstr_b200.automata import StateAutomata
+from warpstr_b200.config import CallerConfig, RescalerConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cc, rc, name='HD', n=6, seed=70, noise=0.2, flank=110, engine=None):
+    from warpstr_b200.caller import CallerEngine
+    eng = CallerEngine(cc, rc)
+    locus = synth.make_locus(name, seed=seed, flank_length=flank)
+    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    ids = [eng.add_automaton(s, flank) for s in stas]
+    reads = synth.make_reads(locus, n, seed=seed + 1, noise=noise)
+    res = eng.call_batch([r.signal for r in reads], [ids[int(r.reverse)] for r in reads],
+                         [r.reverse for r in reads], engine=engine)
+    kn = co.Knobs(cc.min_values_per_state, cc.states_in_segment, rc.reps_as_one, rc.threshold, rc.max_std, rc.method)
+    want = [co.run_read(r.signal, co.tables_from(stas[int(r.reverse)]), flank, r.reverse, kn, impl='c') for r in reads]
+    return res, want
+
+
+@pytest.mark.parametrize('mv', [3, 4, 5])
+def test_min_values_per_state(built_lib, oracle_c, mv):
+    res, want = _run(CallerConfig(min_values_per_state=mv), RescalerConfig())
+    for g, w in zip(res, want):
+        assert g.seq == w.seq and g.resc_seq == w.resc_seq
+        assert g.cost == w.cost and g.resc_cost == w.resc_cost
+
+
+@pytest.mark.parametrize('sis', [3, 6, 9])
+def test_states_in_segment(built_lib, oracle_c, sis):
+    res, want = _run(CallerConfig(states_in_segment=sis), RescalerConfig(), noise=0.3)
+    for g, w in zip(res, want):
+        assert g.resc_seq == w.resc_seq and g.resc_cost == w.resc_cost
+
+
+@pytest.mark.parametrize('thr,mstd', [(0.3, 0.5), (0.5, 0.25), (0.8, 0.8)])
+def test_rescaling_thresholds(built_lib, oracle_c, thr, mstd):
+    res, want = _run(CallerConfig(), RescalerConfig(threshold=thr, max_std=mstd))
+    for g, w in zip(res, want):
+        assert g.resc_seq == w.resc_seq and g.resc_cost == w.resc_cost
+
+
+def test_spline_with_interior_knots_goes_to_the_host(built_lib, oracle_c):
+    """threshold > 1 admits pairs whose residual can exceed s = m: FITPACK then adds knots;
+    the device flags the read (status 5) and the host evaluates it with scipy -- same result
+    as the reference either way."""
+    res, want = _run(CallerConfig(), RescalerConfig(threshold=3.0, max_std=3.0), noise=0.9, n=8)
+    for g, w in zip(res, want):
+        assert g.resc_seq == w.resc_seq
+        assert g.resc_cost == pytest.approx(w.resc_cost, rel=1e-9)
+
+
+@pytest.mark.parametrize('rc', [RescalerConfig(method='median'), RescalerConfig(reps_as_one=True)])
+def test_host_engine_variants(built_lib, oracle_c, rc):
+    res, want = _run(CallerConfig(), rc, n=3)
+    for g, w in zip(res, want):
+        assert g.seq == w.seq and g.resc_seq == w.resc_seq
+        assert g.resc_cost == pytest.approx(w.resc_cost, rel=1e-9)
+
+
+def test_unsupported_mv_is_reported(built_lib):
+    from warpstr_b200 import _lib
+    from warpstr_b200.caller import CallerEngine
+    eng = CallerEngine(CallerConfig(min_values_per_state=7))
+    locus = synth.make_locus('AAAT', seed=1)
+    with pytest.raises(_lib.WarpstrError):
+        eng.add_automaton(StateAutomata(locus.template_regex), 110)
