@@ -101,3 +101,33 @@ def test_engine_raises_reference_exception_types(built_lib):
         eng.call_batch([rd.signal[:3]], [a], [False])
     ok = eng.call_batch([rd.signal], [a], [False])
     assert len(ok[0].resc_seq) == rd.truth_len
+
+
+def test_main_wrapper_files(built_lib, tmp_path):
+    """overview.csv in -> calls on the GPU -> overview.csv / FASTA / complex-unit CSV out, through
+    the reference-shaped driver (wrapper.py:17-41), for a complex (multi-unit) locus."""
+    import pandas as pd
+    from oracle import caller_oracle as co
+    from warpstr_b200 import synth
+    from warpstr_b200.wrapper import Locus, ReadSignal, flanks_from_template, main_wrapper
+    sl = synth.make_locus('DM2', seed=8)
+    reads = synth.make_reads(sl, 6, seed=9)
+    d = tmp_path / 'DM2'
+    (d / 'expected_signals').mkdir(parents=True)
+    (d / 'summaries').mkdir()
+    fl = flanks_from_template(sl.left, sl.right)
+    with open(d / 'expected_signals' / 'sequences.csv', 'w') as fh:
+        fh.write('type,sequence\n')
+        fh.write(f'left_flank_template,{fl.template.left}\nright_flank_template,{fl.template.right}\n')
+        fh.write(f'left_flank_reverse,{fl.reverse.left}\nright_flank_reverse,{fl.reverse.right}\n')
+    pd.DataFrame({'read_name': [r.name for r in reads] + ['skipped'], 'run_id': ['x'] * 7,
+                  'reverse': [r.reverse for r in reads] + [False], 'saved': [1] * 6 + [0],
+                  'l_start_raw': [0] * 7, 'r_end_raw': [1] * 7}).to_csv(d / 'overview.csv', index=False)
+    locus = Locus('DM2', sl.sequence, 110, str(d))
+    df, dfc = main_wrapper(locus, 4, workload=[ReadSignal(r.name, r.reverse, r.signal) for r in reads])
+    assert list(df['results'][:6]) == [r.truth_len for r in reads] and df['results'].iloc[6] == -1
+    assert dfc is not None and 'main_CAGG' in dfc.columns and len(dfc) == 6
+    assert os.path.exists(d / 'predictions' / 'sequences' / 'all.fasta')
+    assert os.path.exists(d / 'summaries' / 'state_similarity.csv')
+    back = pd.read_csv(d / 'overview.csv')
+    assert {'results', 'orig', 'dtw_cost1', 'dtw_cost2'} <= set(back.columns)

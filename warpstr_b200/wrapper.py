@@ -207,3 +207,53 @@ class CallerWrapper:
                     break
                 rest = nxt
         return results
+
+
+def get_workload(df_overview, path: str, spike_removal: str = 'Brute') -> List[ReadSignal]:
+    """Reads of the locus with their normalised STR windows (reference: wrapper.py:44-54).
+    The raw int16 signal of every saved read is pulled from its annotated single-read fast5
+    (needs h5py, exactly as the reference does) and all reads are spike-filtered, MAD
+    normalised and sliced in one GPU launch."""
+    try:
+        import h5py
+    except ImportError as exc:
+        raise ImportError('reading fast5 files needs h5py (with the VBZ plugin for compressed files); '
+                          'pass an explicit workload to main_wrapper instead') from exc
+    from .normalize import normalize_windows
+    names, revs, raws, wins = [], [], [], []
+    for row in df_overview.itertuples():
+        if row.saved:
+            fpath = os.path.join(path, tmpl.FAST5_SUBDIR, str(row.run_id), tmpl.ANNOT_SUBDIR, row.Index + '.fast5')
+            with h5py.File(fpath, 'r') as fh:
+                rname = list(fh['Raw']['Reads'].keys())[0]
+                raws.append(np.asarray(fh['Raw']['Reads'][rname]['Signal']))
+            names.append(row.Index)
+            revs.append(bool(row.reverse))
+            wins.append((int(row.l_start_raw), int(row.r_end_raw)))
+    sigs = normalize_windows(raws, wins, spike_removal)
+    return [ReadSignal(n, r, s) for n, r, s in zip(names, revs, sigs)]
+
+
+def main_wrapper(locus: Locus, threads: int = 1, config: Optional[Config] = None,
+                 workload: Optional[Sequence[ReadSignal]] = None, flanks: Optional[Flanks] = None,
+                 engine: Optional[CallerEngine] = None):
+    """The caller step of one locus (reference: wrapper.py:17-41): overview.csv in, calls on the
+    GPU, overview.csv / FASTA / complex-unit CSV out.  Plots are not produced.  ``workload``
+    (one ReadSignal per saved overview row, in row order) bypasses the fast5 reading."""
+    from .overview import load_overview, store_collapsed, store_results
+    overview_path, df_overview = load_overview(locus.path)
+    cc = config.caller_config if config is not None else CallerConfig()
+    if workload is None:
+        workload = get_workload(df_overview, locus.path, cc.spike_removal)
+    call_wrapper = CallerWrapper(locus, threads, flanks=flanks, config=config, engine=engine)
+    results = call_wrapper.run(workload)
+    seq_results = [(r.seq, r.resc_seq) for r in results]
+    cost_results = [(r.cost, r.resc_cost) for r in results]
+    df_overview = store_results(overview_path, df_overview, seq_results, cost_results, locus.path)
+    df_collapsed = None
+    if len(call_wrapper.units) > 1:
+        print(f'Running complex genotyping as complex repeat units present: {call_wrapper.units}')
+        collapsed = [call_wrapper.collapse_repeats(s[1]) for s in seq_results]
+        df_collapsed = store_collapsed(collapsed, call_wrapper.units, call_wrapper.repeat_units,
+                                       [bool(r.reverse) for r in workload], locus.path)
+    return df_overview, df_collapsed
