@@ -131,3 +131,22 @@ def test_main_wrapper_files(built_lib, tmp_path):
     assert os.path.exists(d / 'summaries' / 'state_similarity.csv')
     back = pd.read_csv(d / 'overview.csv')
     assert {'results', 'orig', 'dtw_cost1', 'dtw_cost2'} <= set(back.columns)
+
+
+def test_expected_signal_step_files(built_lib, tmp_path):
+    """sequences.csv + expected-signal text files (Squiggler.process_locus), read back by load_flanks."""
+    from warpstr_b200.locus import write_expected_signals
+    from warpstr_b200.pore_model import get_pore_model
+    from warpstr_b200.wrapper import load_flanks
+    rng = np.random.default_rng(3)
+    chrom = ''.join(rng.choice(list('ACGT'), 400)) + 'CAG' * 20 + ''.join(rng.choice(list('ACGT'), 400))
+    fa = tmp_path / 'g.fa'
+    fa.write_text('>chr9\n' + '\n'.join(chrom[i:i + 50] for i in range(0, len(chrom), 50)) + '\n')
+    seqs = write_expected_signals(str(tmp_path / 'L'), 'chr9:401-460', str(fa), 110)
+    assert seqs['temp_ref_pattern'] == 'CAG' * 20 and seqs['left_flank_template'] == chrom[290:400]
+    fl = load_flanks(str(tmp_path / 'L'))
+    assert fl.template.right == chrom[460:570] and fl.reverse.left == seqs['left_flank_reverse']
+    lv = np.loadtxt(tmp_path / 'L' / 'expected_signals' / 'left_flank_template.txt')
+    pm = get_pore_model()
+    want = pm.get_values([seqs['left_flank_template'][i:i + 6] for i in range(105)])
+    assert lv.shape == (105,) and np.allclose(lv, want, atol=1e-6)

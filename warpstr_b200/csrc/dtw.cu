@@ -519,7 +519,9 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
         }
         if (lane == 0) p.status[m.read] = WSTR_READ_OK;
         __syncwarp();   // this warp's direction words are visible to all of its lanes
+#ifndef WSTR_NO_TRACEBACK   // (experiment switch: time the fill alone)
         traceback_warp<K>(A, T, dir, mw_ptr, p.trace + m.sig_off, p.status + m.read, lane);
+#endif
     }
 }
 
