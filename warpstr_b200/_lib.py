@@ -152,7 +152,7 @@ class DeviceAutomaton:
     def info(self) -> dict:
         buf = np.zeros(7, dtype=np.int32)
         check(lib().wstr_automaton_info(self.handle, _ptr(buf, c_i32p), 7), 'wstr_automaton_info')
-        keys = ('states_per_lane', 'dir_words_per_row', 'chain_slots', 'generic_slots', 'n_states', 'n_edges',
+        keys = ('states_per_lane', 'dir_bits_per_row', 'chain_slots', 'generic_slots', 'n_states', 'n_edges',
                 'generic_states')
         return dict(zip(keys, (int(x) for x in buf)))
 

@@ -281,7 +281,7 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     };
 
     std::vector<uint32_t> lane_tab(32 * WSTR_LANE_TAB_STRIDE, 0u);
-    std::vector<int16_t> pred_tab((size_t)NP * WSTR_PRED_STRIDE, (int16_t)-1);
+    std::vector<int32_t> pred_tab((size_t)NP * WSTR_PRED_STRIDE, -1);   // (state << 16) | position
     std::vector<double> v_pos(NP, 0.0);
     std::vector<int16_t> sop(NP, -1);
     const int boundary = flank_length - 10;
@@ -304,7 +304,7 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
             if (deg == 1) {
                 const int pstate = in_idx[in_ptr[j]];
                 const int ppos = L.pos_of_state[pstate];
-                pred_tab[(size_t)pos * WSTR_PRED_STRIDE + 1] = (int16_t)ppos;
+                pred_tab[(size_t)pos * WSTR_PRED_STRIDE + 1] = (pstate << 16) | ppos;
                 if (u == 0) {
                     const int q = published(pstate);
                     if (q < 0) return WSTR_ERR_UNSUPPORTED;    // layout invariant
@@ -323,7 +323,7 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
                     const int pstate = in_idx[in_ptr[j] + r];
                     q = published(pstate);
                     if (q < 0) return WSTR_ERR_UNSUPPORTED;    // layout invariant
-                    pred_tab[(size_t)pos * WSTR_PRED_STRIDE + 1 + r] = (int16_t)L.pos_of_state[pstate];
+                    pred_tab[(size_t)pos * WSTR_PRED_STRIDE + 1 + r] = (pstate << 16) | L.pos_of_state[pstate];
                 }
                 packed |= (uint32_t)q << (8 * r);
             }
@@ -341,13 +341,13 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
         return o;
     };
     const size_t o_v = take(sizeof(double) * NP), o_sop = take(sizeof(int16_t) * NP),
-                 o_lt = take(sizeof(uint32_t) * lane_tab.size()), o_pt = take(sizeof(int16_t) * pred_tab.size()),
+                 o_lt = take(sizeof(uint32_t) * lane_tab.size()), o_pt = take(sizeof(int32_t) * pred_tab.size()),
                  o_val = take(sizeof(double) * S), o_sq = take(sizeof(int32_t) * S), o_rm = take(S), o_lb = take(S);
     std::vector<unsigned char> blob(off, 0);
     memcpy(blob.data() + o_v, v_pos.data(), sizeof(double) * NP);
     memcpy(blob.data() + o_sop, sop.data(), sizeof(int16_t) * NP);
     memcpy(blob.data() + o_lt, lane_tab.data(), sizeof(uint32_t) * lane_tab.size());
-    memcpy(blob.data() + o_pt, pred_tab.data(), sizeof(int16_t) * pred_tab.size());
+    memcpy(blob.data() + o_pt, pred_tab.data(), sizeof(int32_t) * pred_tab.size());
     memcpy(blob.data() + o_val, values, sizeof(double) * S);
     memcpy(blob.data() + o_sq, seq_idx, sizeof(int32_t) * S);
     if (rep_mask) memcpy(blob.data() + o_rm, rep_mask, S);
@@ -364,17 +364,28 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     d.v_pos = reinterpret_cast<const double *>(base + o_v);
     d.state_of_pos = reinterpret_cast<const int16_t *>(base + o_sop);
     d.lane_tab = reinterpret_cast<const uint32_t *>(base + o_lt);
-    d.pred_tab = reinterpret_cast<const int16_t *>(base + o_pt);
+    d.pred_tab = reinterpret_cast<const int32_t *>(base + o_pt);
     d.K = K;
     d.KC = KC;
     d.KG = KG;
     d.DEG = L.DEG;
-    d.W = (K + 7) / 8;
+    d.NB = KC + KG * L.DEG;          // direction bits per lane and row (dtw.cu: DirFmt)
+    d.RPW = 32 / d.NB;
     d.S = S;
     d.end_pos = L.pos_of_state[endstate];
     d.mv = mv;
     d.th1 = 6 * boundary;
     d.band6 = 6 * boundary;
+    // The end band skips the states with seq_idx < after.  If none of them has an incoming edge
+    // from a state outside that set, the skipped cells stay +inf on their own once the values
+    // computed before the band have left the pipeline (mv rows), and the kernel drops the
+    // per-cell band test from there on.
+    d.band_closed = 1;
+    for (int j = 0; j < S; ++j) {
+        if (seq_idx[j] >= after) continue;
+        for (int e = in_ptr[j]; e < in_ptr[j + 1]; ++e)
+            if (seq_idx[in_idx[e]] >= after) d.band_closed = 0;
+    }
     for (int c = 0; c <= mv; ++c) d.init_pos[c] = L.pos_of_state[c];
 
     wstr_automaton *a = new wstr_automaton();
@@ -422,7 +433,7 @@ extern "C" int wstr_automaton_destroy(wstr_automaton *a) {
 
 extern "C" int wstr_automaton_info(const wstr_automaton *a, int32_t *info, int32_t n_info) {
     if (!a || !info) return WSTR_ERR_INVALID_ARGUMENT;
-    const int32_t vals[7] = {a->dev.K, a->dev.W, a->dev.KC, a->dev.KG, a->dev.S, a->n_edges, a->n_generic};
+    const int32_t vals[7] = {a->dev.K, a->dev.NB, a->dev.KC, a->dev.KG, a->dev.S, a->n_edges, a->n_generic};
     for (int i = 0; i < n_info && i < 7; ++i) info[i] = vals[i];
     return WSTR_OK;
 }
@@ -458,7 +469,10 @@ WsPlan plan_workspace(int n_automata, int n_reads) {
     return w;
 }
 
-inline int64_t dir_words(const wstr_automaton *a, int T) { return (int64_t)T * a->dev.W * 32; }
+// direction words of one read: RPW rows share a word per lane (dtw.cu: DirFmt)
+inline int64_t dir_words(const wstr_automaton *a, int T) {
+    return ((int64_t)T + a->dev.RPW - 1) / a->dev.RPW * 32;
+}
 
 }  // namespace
 

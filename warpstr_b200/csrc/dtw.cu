@@ -23,9 +23,10 @@
 //
 // The read's signal is streamed through shared memory in 1 KB tiles with 1-D bulk async
 // copies (cp.async.bulk + mbarrier, TMA engine) two tiles ahead of the row loop.
-// Output: one 4-bit direction code per cell (0 stay, c>0 = c-th incoming edge), packed 8 per
-// 32-bit word, stored row-major [row][word][lane] so that every row is one coalesced
-// 128-byte line per word.  D itself never leaves the SM.
+// Output: a direction code per cell (1 bit for a chain state, DEG bits for a generic one),
+// the codes of one lane and 32/NB consecutive rows packed in one 32-bit word, stored
+// [word row][lane] so that every word row is one coalesced 128-byte line (see DirFmt).
+// D itself never leaves the SM.
 #include "wstr_internal.h"
 
 namespace {
@@ -115,9 +116,27 @@ struct LaneConsts {
 template <int KG>
 __host__ __device__ constexpr int q_row_len() { return 32 * KG + 40; }
 
+// Direction codes.  Per cell a small mask of the candidates that took the lead in turn (bit r =
+// incoming edge r, tried in list order, so the winner is the highest set bit; 0 = stay): one
+// bit for a chain slot, DEG bits for a generic slot, NB = KC + KG*DEG bits per lane and row.
+// RPW = 32/NB consecutive rows share one 32-bit word per lane (row i: word i/RPW, bit field
+// (i%RPW)*NB); a word row [32 lanes] is one coalesced 128-byte line.  HD/FMR1/C9orf72 (6,2,2):
+// 10 bits, 3 rows per word = 0.17 B per cell.
+template <int KC, int KG, int DEG>
+struct DirFmt {
+    static constexpr int NB = KC + KG * DEG;
+    static constexpr int RPW = 32 / NB;
+    static_assert(NB <= 32 && RPW >= 1, "direction codes of one row must fit a 32-bit word");
+};
+
+// running output position of one lane
+struct DirOut {
+    uint32_t acc;      // bits collected for the current word
+    int sh;            // bit offset of the next row inside it
+    uint32_t *ptr;     // where the current word goes
+};
+
 // best = min(best, cand) with the reference's strict '<'; when cand wins, OR `bit` into codes.
-// Per cell the 4-bit code is a mask of the candidates that took the lead in turn (bit r =
-// incoming edge r); candidates are tried in list order, so the winner is the highest set bit.
 __device__ __forceinline__ void take_min(double &best, uint32_t &codes, const double cand, const uint32_t bit) {
     asm("{\n"
         ".reg .pred p;\n"
@@ -132,13 +151,15 @@ __device__ __forceinline__ void take_min(double &best, uint32_t &codes, const do
 // One DP row at pipeline phase PH (leaves the state at phase PH+1).
 // SHORT: this row allows dwell mv-1 (masked row of the second pass).
 // BAND: the end band is active (caller.py:223-224).
+// SUB >= 0: the row's position inside its direction word is known at compile time (the word
+//   is stored after its last row); SUB < 0: taken from o.sh.
 //   Qpub = &Q[lane] of this row's published buffer, Qrow = the buffer itself
-template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, int PH>
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, int PH, int SUB>
 __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc, const double x,
-                                       double *__restrict__ Qpub, const double *__restrict__ Qrow,
-                                       uint32_t *__restrict__ dir_lane) {
+                                       double *__restrict__ Qpub, const double *__restrict__ Qrow, DirOut &o) {
     constexpr int K = KC + KG;
-    constexpr int W = (K + 7) / 8;
+    constexpr int NB = DirFmt<KC, KG, DEG>::NB, RPW = DirFmt<KC, KG, DEG>::RPW;
+    constexpr int B0 = SUB >= 0 ? SUB * NB : 0;      // bit offset of this row's field in `codes`
     const double INF = dinf();
 
     // what other lanes may read this row: my generic states and my chain tail
@@ -147,9 +168,7 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
     Qpub[KG * 32] = offer<K, MV, SHORT, PH>(s, KC - 1);
     __syncwarp();
 
-    uint32_t codes[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) codes[w] = 0u;
+    uint32_t codes = SUB >= 0 ? o.acc : 0u;
 
     // ---- chain slots: stay or the single incoming edge -----------------------------------
     double qprev = *reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(Qrow) + lc.src0);
@@ -159,11 +178,11 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
         const double qhere = offer<K, MV, SHORT, PH>(s, k);
         const double stay = s.D[k] + ae;
         double best = stay;
-        take_min(best, codes[k >> 3], qprev + ae, 1u << (4 * (k & 7)));
+        take_min(best, codes, qprev + ae, 1u << (B0 + k));
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
                 best = INF;
-                codes[k >> 3] &= ~(0xfu << (4 * (k & 7)));
+                codes &= ~(1u << (B0 + k));
             }
         }
         advance<K, MV, PH>(s, k, ae, stay);
@@ -181,34 +200,51 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
 #pragma unroll
         for (int r = 0; r < DEG; ++r) {
             const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
-            take_min(best, codes[k >> 3], Qrow[idx] + ae, 1u << (4 * (k & 7) + r));
+            take_min(best, codes, Qrow[idx] + ae, 1u << (B0 + KC + g * DEG + r));
         }
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
                 best = INF;
-                codes[k >> 3] &= ~(0xfu << (4 * (k & 7)));
+                codes &= ~(((1u << DEG) - 1u) << (B0 + KC + g * DEG));
             }
         }
         advance<K, MV, PH>(s, k, ae, stay);
         s.D[k] = best;
     }
-#pragma unroll
-    for (int w = 0; w < W; ++w) dir_lane[w * 32] = codes[w];
+
+    if (SUB >= 0) {
+        if (SUB == RPW - 1) {
+            *o.ptr = codes;
+            o.ptr += 32;
+            o.acc = 0u;
+        } else {
+            o.acc = codes;
+        }
+    } else {
+        o.acc |= codes << o.sh;
+        o.sh += NB;
+        if (o.sh > 32 - NB) {
+            *o.ptr = o.acc;
+            o.ptr += 32;
+            o.acc = 0u;
+            o.sh = 0;
+        }
+    }
 }
 
 // mv-1 consecutive rows: every role returns to its register, nothing has to be moved.
 // xv holds the rows' samples (fetched one cycle ahead by the caller).
-template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, int PH = 0>
+// ALIGNED: the cycle covers exactly one direction word (RPW == mv-1, entered with o.sh == 0).
+template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, bool ALIGNED, int PH = 0>
 __device__ __forceinline__ void dp_rows_cycle(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
                                               const double (&xv)[MV - 1], double *__restrict__ Qlane,
-                                              const double *__restrict__ Qbase,
-                                              uint32_t *__restrict__ dir_lane) {
-    constexpr int W = (KC + KG + 7) / 8;
+                                              const double *__restrict__ Qbase, DirOut &o) {
     constexpr int QL = q_row_len<KG>();
-    dp_row<KC, KG, DEG, MV, SHORT, BAND, PH>(s, lc, xv[PH], Qlane + PH * QL, Qbase + PH * QL,
-                                            dir_lane + PH * (W * 32));
+    constexpr int RPW = DirFmt<KC, KG, DEG>::RPW;
+    constexpr int SUB = RPW == 1 ? 0 : (ALIGNED ? PH : -1);
+    dp_row<KC, KG, DEG, MV, SHORT, BAND, PH, SUB>(s, lc, xv[PH], Qlane + PH * QL, Qbase + PH * QL, o);
     if constexpr (PH + 1 < MV - 1)
-        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, PH + 1>(s, lc, xv, Qlane, Qbase, dir_lane);
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, ALIGNED, PH + 1>(s, lc, xv, Qlane, Qbase, o);
 }
 
 // a single row from phase 0 back to phase 0 (registers rotated by hand; used for the few rows
@@ -216,9 +252,10 @@ __device__ __forceinline__ void dp_rows_cycle(LaneState<KC + KG, MV> &s, const L
 template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
 __device__ __forceinline__ void dp_row_single(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc, const double x,
                                               double *__restrict__ Qlane, const double *__restrict__ Qbase,
-                                              uint32_t *__restrict__ dir_lane) {
+                                              DirOut &o) {
     constexpr int K = KC + KG;
-    dp_row<KC, KG, DEG, MV, SHORT, BAND, 0>(s, lc, x, Qlane, Qbase, dir_lane);
+    constexpr int SUB = DirFmt<KC, KG, DEG>::RPW == 1 ? 0 : -1;
+    dp_row<KC, KG, DEG, MV, SHORT, BAND, 0, SUB>(s, lc, x, Qlane, Qbase, o);
     __syncwarp();   // the next row publishes into the same buffer
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -233,12 +270,18 @@ __device__ __forceinline__ void dp_row_single(LaneState<KC + KG, MV> &s, const L
 template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND>
 __device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
                                            const double *__restrict__ xs, const int tile0, int i0, const int i1,
-                                           double *__restrict__ Qlane, const double *__restrict__ Qbase,
-                                           uint32_t *__restrict__ dir_lane) {
-    constexpr int W = (KC + KG + 7) / 8;
+                                           double *__restrict__ Qlane, const double *__restrict__ Qbase, DirOut &o) {
     constexpr int CY = MV - 1;
+    constexpr int RPW = DirFmt<KC, KG, DEG>::RPW;
+    constexpr bool ALIGNED = RPW == CY && RPW > 1;
     const double *xp = xs + (i0 - tile0);
-    uint32_t *dp = dir_lane + static_cast<int64_t>(i0) * (W * 32);
+    if (ALIGNED) {   // single rows up to the next word boundary, so that every cycle fills one word
+#pragma unroll 1
+        for (; i0 < i1 && o.sh != 0; ++i0) {
+            dp_row_single<KC, KG, DEG, MV, SHORT, BAND>(s, lc, *xp, Qlane, Qbase, o);
+            xp += 1;
+        }
+    }
     double xv[CY], xn[CY];
 #pragma unroll
     for (int j = 0; j < CY; ++j) xn[j] = xp[j];          // may run a few samples past the tile: unused then
@@ -249,15 +292,13 @@ __device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const Lane
             xv[j] = xn[j];
             xn[j] = xp[CY + j];                          // next cycle's samples, ahead of the barriers
         }
-        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND>(s, lc, xv, Qlane, Qbase, dp);
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, ALIGNED>(s, lc, xv, Qlane, Qbase, o);
         xp += CY;
-        dp += CY * (W * 32);
     }
 #pragma unroll 1
     for (; i0 < i1; ++i0) {
-        dp_row_single<KC, KG, DEG, MV, SHORT, BAND>(s, lc, *xp, Qlane, Qbase, dp);
+        dp_row_single<KC, KG, DEG, MV, SHORT, BAND>(s, lc, *xp, Qlane, Qbase, o);
         xp += 1;
-        dp += W * 32;
     }
 }
 
@@ -285,16 +326,16 @@ template <int KC, int KG, int DEG, int MV, bool BAND>
 __device__ __forceinline__ void dp_tile_rows(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
                                              const double *__restrict__ xs, const int tile0, int i0, const int i1,
                                              const uint32_t *__restrict__ mw_ptr, double *__restrict__ Qlane,
-                                             const double *__restrict__ Qbase, uint32_t *__restrict__ dir_lane) {
+                                             const double *__restrict__ Qbase, DirOut &o) {
     if (!mw_ptr) {
-        dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, i1, Qlane, Qbase, dir_lane);
+        dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, i1, Qlane, Qbase, o);
         return;
     }
     while (i0 < i1) {
         uint32_t bit;
         const int b = mask_run_end(mw_ptr, i0, i1, bit);
-        if (bit) dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, tile0, i0, b, Qlane, Qbase, dir_lane);
-        else dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, b, Qlane, Qbase, dir_lane);
+        if (bit) dp_segment<KC, KG, DEG, MV, true, BAND>(s, lc, xs, tile0, i0, b, Qlane, Qbase, o);
+        else dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, b, Qlane, Qbase, o);
         i0 = b;
     }
 }
@@ -306,63 +347,126 @@ __device__ __forceinline__ void dp_tile_rows(LaneState<KC + KG, MV> &s, const La
 // exactly, so following the fill's arg-min with the same priority (stay, then incoming in
 // list order) visits the same cells.
 //
-// Done by the warp that filled the read, right after the fill.  The walk itself is a chain
-// of dependent steps, so the warp fetches 32 rows at a time (lane t holds the word of row
-// i-t for the lane/word the path is currently in; a word carries the codes of 8 states of
-// that lane, so the window stays valid while the path moves along a chain) and walks the
-// window with shuffles; the trace is written 32 samples at a time.  While this warp waits
-// for its window the SM's other warps keep the FP64 pipe busy with their fills.
+// Done by the warp that filled the read, right after the fill.  The direction words are
+// staged through shared memory in windows of WRW word rows (one bulk async copy per word row
+// into a padded slot, a ring of NBUF windows in flight), so the walk never waits on HBM for
+// a dependent step.  Inside a window lane t looks at row hi-t: every lane extracts the code
+// of the path's current state in its own row, one ballot finds the first row that is not a
+// "stay", all rows above it are emitted at once, and only the state changes (one per ~9
+// samples) cost a dependent step.  The trace is written one window at a time.
 // ------------------------------------------------------------------------------------------
-template <int K>
+template <int RPW>
+struct TbGeom {
+    static constexpr int WRW = RPW == 1 ? 16 : 32 / RPW;   // word rows per window (<= 32 DP rows)
+    static constexpr int ROWS = WRW * RPW;                 // DP rows per window
+    static constexpr int STRIDE = 36;                      // words per padded slot (16-byte granules, spreads banks)
+    static constexpr int NBUF = RPW >= 3 ? 5 : 4;          // windows in flight
+    static constexpr int WORDS = NBUF * WRW * STRIDE;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int KC, int KG, int DEG>
 __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int T, const uint32_t *dir,
                                                const uint32_t *mw, int32_t *tr, int32_t *status_slot,
-                                               const int lane) {
-    constexpr int W = (K + 7) / 8;
+                                               const int lane, uint32_t *win, uint64_t *bar, uint32_t &phase_bits) {
+    constexpr int K = KC + KG;
+    constexpr int NB = DirFmt<KC, KG, DEG>::NB, RPW = DirFmt<KC, KG, DEG>::RPW;
+    using G = TbGeom<RPW>;
+    constexpr int WRW = G::WRW, ROWS = G::ROWS, ST = G::STRIDE, NBUF = G::NBUF;
     const int mv = A->mv;
-    const int16_t *sop = A->state_of_pos;
-    const int16_t *pred = A->pred_tab;
+    const int32_t *pred = A->pred_tab;
+    const int wtop = (T - 1) / RPW;                  // last word row
+    const int wmin = mv / RPW;                       // first word row that was written
+    const int nwin = wtop / WRW + 1;
+
+    // window c holds word rows wh-WRW+1 .. wh, wh = wtop - c*WRW; slot s of its buffer = word row wh-s
+    auto issue = [&](int c) {
+        const int b = c % NBUF;
+        const int wh = wtop - c * WRW;
+        int n = wh - wmin + 1;
+        n = n > WRW ? WRW : (n < 0 ? 0 : n);
+        if (lane == 0) mbar_expect_tx(&bar[b], static_cast<uint32_t>(n) * 128u);
+        __syncwarp();
+        const int wr = wh - lane;
+        if (lane < WRW && wr >= wmin)
+            bulk_copy(win + (b * WRW + lane) * ST, dir + static_cast<int64_t>(wr) * 32, 128u, &bar[b]);
+    };
+
     int i = T - 1;
     int pos = A->end_pos;
-    int st = __ldg(sop + pos);
+    int st = __ldg(A->state_of_pos + pos);
     bool failed = false;
-    while (i > 0 && !failed) {
-        const int held_lane = pos / K;
-        int u = pos - held_lane * K;
-        const int held_word = u >> 3;
-        const int row = i - lane;
-        uint32_t w = 0u, mb = 0u;
-        if (row >= mv) w = __ldcg(dir + (static_cast<int64_t>(row) * W + held_word) * 32 + held_lane);
-        if (mw && row >= 0) mb = (__ldg(mw + (row >> 5)) >> (row & 31)) & 1u;
-        int my = -1;
-        int t = 0;
-        while (t < 32 && i - t > 0) {
-            const uint32_t wt = __shfl_sync(FULL, w, t);
-            const uint32_t nib = (wt >> (4 * (u & 7))) & 15u;
-            const uint32_t code = 32u - static_cast<uint32_t>(__clz(nib));   // last candidate that took the lead
-            if (lane == t) my = st;
-            if (code == 0u) {
-                t += 1;
-                continue;
-            }
-            const int back = mv - static_cast<int>(__shfl_sync(FULL, mb, t));
-            const int ppos = __ldg(pred + pos * WSTR_PRED_STRIDE + static_cast<int>(code));
-            if (i - t < back || ppos < 0) {
-                failed = true;
-                break;
-            }
-            const int pst = __ldg(sop + ppos);
-            if (lane > t && lane < t + back) my = pst;
-            for (int r = 32; r < t + back; ++r)       // the skip runs past the window (at most mv-1 rows)
-                if (lane == 0 && r > t) tr[i - r] = pst;
-            t += back;
-            pos = ppos;
-            st = pst;
-            const int nl = pos / K;
-            u = pos - nl * K;
-            if (nl != held_lane || (u >> 3) != held_word) break;   // the window no longer covers the path
+    for (int c = 0; c < nwin && c < NBUF; ++c) issue(c);
+
+    for (int c = 0; c < nwin; ++c) {
+        const int b = c % NBUF;
+        while (!mbar_try_wait(&bar[b], (phase_bits >> b) & 1u)) {
         }
-        if (lane < t && row > 0) tr[row] = my;
-        i -= t;
+        phase_bits ^= 1u << b;
+        const int wh = wtop - c * WRW;
+        const int hi = wh * RPW + RPW - 1;            // may lie past T-1 in the first window
+        const int lo = hi - ROWS + 1 > 0 ? hi - ROWS + 1 : 0;
+        if (i >= lo && i > 0 && !failed) {
+            const int row = hi - lane;
+            const bool mine = lane < ROWS && row >= lo;
+            uint32_t mb = 0u;
+            if (mw && mine && row < T) mb = (__ldg(mw + (row >> 5)) >> (row & 31)) & 1u;
+            const int wr = mine ? row / RPW : wh;
+            const uint32_t *wslot = win + (b * WRW + (wh - wr)) * ST;
+            const int fsh = (row - wr * RPW) * NB;      // this row's bit field inside its word
+            int my = -1;
+            for (;;) {
+                const int hl = pos / K;
+                const int u = pos - hl * K;
+                uint32_t nib = 0u;
+                if (mine && row <= i && row >= mv) {
+                    const uint32_t f = wslot[hl] >> fsh;
+                    nib = u < KC ? (f >> u) & 1u : (f >> (KC + (u - KC) * DEG)) & ((1u << DEG) - 1u);
+                }
+                const uint32_t moves = __ballot_sync(FULL, nib != 0u);
+                if (moves == 0u) {                          // stays down to the window's last row
+                    if (mine && row <= i) my = st;
+                    i = lo - 1;
+                    break;
+                }
+                const int tm = __ffs(moves) - 1;            // lane of the first row that leaves the state
+                const int rm = hi - tm;
+                if (mine && row <= i && row >= rm) my = st; // the stays above it and the row itself
+                const uint32_t nibm = __shfl_sync(FULL, nib, tm);
+                const int code = 32 - __clz(nibm);          // last candidate that took the lead
+                const int back = mv - static_cast<int>(__shfl_sync(FULL, mb, tm));
+                const int32_t pp = __ldg(pred + pos * WSTR_PRED_STRIDE + code);
+                if (rm < back || pp < 0) {
+                    failed = true;
+                    break;
+                }
+                const int pst = pp >> 16;
+                // the skipped rows rm-1 .. rm-back+1 belong to the predecessor
+                if (mine && row < rm && row > rm - back) my = pst;
+                if (rm - back + 1 < lo) {                   // ... some of them lie below this window
+                    const int r = lo - 1 - lane;
+                    if (lane < back - 1 && r > rm - back) tr[r] = pst;
+                }
+                i = rm - back;
+                pos = pp & 0xffff;
+                st = pst;
+                if (i < lo || i <= 0) break;
+            }
+            if (mine && my >= 0) tr[row] = my;
+        }
+        __syncwarp();                                       // every lane is done with this buffer
+        if (c + NBUF < nwin) issue(c + NBUF);
     }
     if (lane == 0) {
         if (failed) *status_slot = WSTR_READ_BACKTRACK;
@@ -370,12 +474,15 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
     }
 }
 
-// per-warp shared memory: [sig 2 x CH f64][published rows 2 x q_row_len f64][2 mbarriers]
-template <int KG, int MV>
+// per-warp shared memory
+template <int KC, int KG, int DEG, int MV>
 struct alignas(16) FillSmem {
+    using G = TbGeom<DirFmt<KC, KG, DEG>::RPW>;
     double sig[2][CH];                   // look-ahead reads may run up to 2*(mv-1) samples past a tile (into Q: unused)
     double Q[MV - 1][q_row_len<KG>()];   // one published buffer per pipeline phase
-    uint64_t bar[2];
+    uint32_t win[G::WORDS];              // traceback windows
+    uint64_t bar[2];                     // signal tiles
+    uint64_t tbar[G::NBUF];              // traceback windows
 };
 
 #ifndef WSTR_K8_BLOCKS
@@ -391,19 +498,22 @@ template <int KC, int KG, int DEG, int MV>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int K = KC + KG;
-    constexpr int W = (K + 7) / 8;
+    constexpr int NB = DirFmt<KC, KG, DEG>::NB, RPW = DirFmt<KC, KG, DEG>::RPW;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FillSmem<KG, MV> &sm = reinterpret_cast<FillSmem<KG, MV> *>(smem_raw)[warp];
+    using Smem = FillSmem<KC, KG, DEG, MV>;
+    Smem &sm = reinterpret_cast<Smem *>(smem_raw)[warp];
     const double INF = dinf();
 
     if (lane == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
+        for (int b = 0; b < Smem::G::NBUF; ++b) mbar_init(&sm.tbar[b], 1);
         fence_barrier_init();
     }
     for (int e = lane; e < (MV - 1) * q_row_len<KG>(); e += 32) (&sm.Q[0][0])[e] = INF;   // incl. the +inf cell
     __syncwarp();
     uint32_t uses0 = 0, uses1 = 0;   // completed phases of the two tile barriers
+    uint32_t tb_phase = 0;           // parity bits of the traceback window barriers
 
     LaneState<K, MV> s;
     LaneConsts<KG> lc;
@@ -479,9 +589,16 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
         }
 
         const int band_start = max(A->th1, T - A->band6 + 1);
+        // mv rows into the band every value computed before it has left the pipelines; if no edge
+        // enters the skipped set from outside, its cells then stay +inf (and their codes 0) without
+        // the per-cell test
+        const int band_free = A->band_closed ? band_start + MV : T;
         const uint32_t *mw_ptr = p.maskbits ? p.maskbits + m.mask_off : nullptr;
         uint32_t *dir = p.dir + m.dir_off;
-        uint32_t *dir_lane = dir + lane;
+        DirOut o;   // rows below mv leave their bits 0
+        o.acc = 0u;
+        o.sh = (MV % RPW) * NB;
+        o.ptr = dir + (MV / RPW) * 32 + lane;
         double *Qlane = &sm.Q[0][0] + lane;
         const double *Qbase = &sm.Q[0][0];
 
@@ -500,17 +617,19 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
             const double *xs = sm.sig[c & 1];
             const int i_begin = c == 0 ? MV : c * CH;
             const int i_end = min(T, (c + 1) * CH);
-            const int i_mid = min(max(band_start, i_begin), i_end);   // rows from here on are banded
-            if (i_begin < i_mid)
-                dp_tile_rows<KC, KG, DEG, MV, false>(s, lc, xs, c * CH, i_begin, i_mid, mw_ptr, Qlane, Qbase,
-                                                     dir_lane);
-            if (i_mid < i_end)
-                dp_tile_rows<KC, KG, DEG, MV, true>(s, lc, xs, c * CH, i_mid, i_end, mw_ptr, Qlane, Qbase,
-                                                    dir_lane);
+            // rows [band_start, band_free) carry the end band's per-cell test, the others do not
+            for (int a = i_begin; a < i_end;) {
+                const bool banded = a >= band_start && a < band_free;
+                const int e = banded ? min(i_end, band_free) : (a < band_start ? min(i_end, band_start) : i_end);
+                if (banded) dp_tile_rows<KC, KG, DEG, MV, true>(s, lc, xs, c * CH, a, e, mw_ptr, Qlane, Qbase, o);
+                else dp_tile_rows<KC, KG, DEG, MV, false>(s, lc, xs, c * CH, a, e, mw_ptr, Qlane, Qbase, o);
+                a = e;
+            }
             __syncwarp();                          // every lane is done with this tile
             if (c + 2 < nchunks) issue(c + 2);     // refill it
         }
 
+        if (o.sh != 0) *o.ptr = o.acc;   // the last, partly filled word
         if (p.end_cost) {
             const int ep = A->end_pos;
 #pragma unroll
@@ -520,7 +639,8 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
         if (lane == 0) p.status[m.read] = WSTR_READ_OK;
         __syncwarp();   // this warp's direction words are visible to all of its lanes
 #ifndef WSTR_NO_TRACEBACK   // (experiment switch: time the fill alone)
-        traceback_warp<K>(A, T, dir, mw_ptr, p.trace + m.sig_off, p.status + m.read, lane);
+        traceback_warp<KC, KG, DEG>(A, T, dir, mw_ptr, p.trace + m.sig_off, p.status + m.read, lane, sm.win, sm.tbar,
+                                    tb_phase);
 #endif
     }
 }
@@ -528,7 +648,7 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
 template <int KC, int KG, int DEG, int MV>
 int launch_fill_t(const FillParams &p, cudaStream_t s) {
     static int grid_cap = 0;
-    const int smem = static_cast<int>(sizeof(FillSmem<KG, MV>)) * WSTR_WARPS_PER_CTA;
+    const int smem = static_cast<int>(sizeof(FillSmem<KC, KG, DEG, MV>)) * WSTR_WARPS_PER_CTA;
     if (grid_cap == 0) {
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -13,7 +13,7 @@
 #endif
 #define WSTR_MAX_DEG 4           // incoming edges of a generic-slot state
 #define WSTR_LANE_TAB_STRIDE 8   // u32 per lane: band bits, slot-0 source, gsrc[0..5]
-#define WSTR_PRED_STRIDE 8       // i16 per position: predecessor position by direction code
+#define WSTR_PRED_STRIDE 8       // i32 per position: predecessor (state << 16 | position) by direction code
 
 // Device view of one automaton laid out for the warp-per-read kernel (see dtw.cu).
 // Position p = lane*K + u; u < KC is a chain slot, u >= KC the generic slot u-KC.
@@ -23,14 +23,15 @@ struct DevAutomaton {
     const double *v_pos;             // [32*K] level per position (0 for padding)
     const int16_t *state_of_pos;     // [32*K] state index, -1 = padding
     const uint32_t *lane_tab;        // [32][WSTR_LANE_TAB_STRIDE]
-    const int16_t *pred_tab;         // [32*K][WSTR_PRED_STRIDE]: predecessor position for code c (-1 none)
+    const int32_t *pred_tab;         // [32*K][WSTR_PRED_STRIDE]: (state << 16) | position of the predecessor for code c (-1 none)
     int32_t K, KC, KG, DEG;
-    int32_t W;                       // direction words per lane per row (4 bits per slot)
+    int32_t NB, RPW;                 // direction bits per lane and row; rows per 32-bit word (32/NB)
     int32_t S;                       // states
     int32_t end_pos;                 // position of the end state
     int32_t mv;                      // min_values_per_state
     int32_t th1;                     // 6*(flank_length-10)
     int32_t band6;                   // 6*(flank_length-10) (second threshold = T - band6)
+    int32_t band_closed;             // no edge leads from outside the end band's skipped set into it
     int32_t init_pos[WSTR_MAX_MV + 1];  // positions of states 0..mv (row-0 initialisation)
 };
 
