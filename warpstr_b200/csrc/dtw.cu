@@ -136,16 +136,20 @@ struct DirOut {
     uint32_t *ptr;     // where the current word goes
 };
 
-// best = min(best, cand) with the reference's strict '<'; when cand wins, OR `bit` into codes.
-__device__ __forceinline__ void take_min(double &best, uint32_t &codes, const double cand, const uint32_t bit) {
+// min(best, cand) with the reference's strict '<'; when cand wins, OR `bit` into codes.
+// (The result is a fresh register on purpose: tying it to `best` would force a copy whenever
+// best is still needed, as the stay value is for the pipeline.)
+__device__ __forceinline__ double take_min(const double best, uint32_t &codes, const double cand, const uint32_t bit) {
+    double out;
     asm("{\n"
         ".reg .pred p;\n"
-        "setp.lt.f64 p, %2, %0;\n"
-        "@p mov.f64 %0, %2;\n"
-        "@p or.b32 %1, %1, %3;\n"
+        "setp.lt.f64 p, %2, %3;\n"
+        "selp.f64 %0, %2, %3, p;\n"
+        "@p or.b32 %1, %1, %4;\n"
         "}\n"
-        : "+d"(best), "+r"(codes)
-        : "d"(cand), "r"(bit));
+        : "=d"(out), "+r"(codes)
+        : "d"(cand), "d"(best), "r"(bit));
+    return out;
 }
 
 // One DP row at pipeline phase PH (leaves the state at phase PH+1).
@@ -171,14 +175,16 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
     uint32_t codes = SUB >= 0 ? o.acc : 0u;
 
     // ---- chain slots: stay or the single incoming edge -----------------------------------
-    double qprev = *reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(Qrow) + lc.src0);
+    // (last slot first: a slot's candidate is the old pipeline value of the slot below it, which
+    // is then still untouched, so every update can happen in place)
+    const double qfirst = *reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(Qrow) + lc.src0);
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
+    for (int k = KC - 1; k >= 0; --k) {
         const double ae = fabs(x - s.v[k]);
-        const double qhere = offer<K, MV, SHORT, PH>(s, k);
+        const double qprev = k > 0 ? offer<K, MV, SHORT, PH>(s, k > 0 ? k - 1 : 0) : qfirst;
         const double stay = s.D[k] + ae;
         double best = stay;
-        take_min(best, codes, qprev + ae, 1u << (B0 + k));
+        best = take_min(best, codes, qprev + ae, 1u << (B0 + k));
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
                 best = INF;
@@ -187,7 +193,6 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
         }
         advance<K, MV, PH>(s, k, ae, stay);
         s.D[k] = best;
-        qprev = qhere;
     }
 
     // ---- generic slots: stay, then up to DEG incoming edges in list order --------------------
@@ -200,7 +205,7 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
 #pragma unroll
         for (int r = 0; r < DEG; ++r) {
             const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
-            take_min(best, codes, Qrow[idx] + ae, 1u << (B0 + KC + g * DEG + r));
+            best = take_min(best, codes, Qrow[idx] + ae, 1u << (B0 + KC + g * DEG + r));
         }
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
@@ -233,18 +238,20 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
 }
 
 // mv-1 consecutive rows: every role returns to its register, nothing has to be moved.
-// xv holds the rows' samples (fetched one cycle ahead by the caller).
+// xv holds the rows' samples; each is replaced by the next cycle's as soon as its row is done.
 // ALIGNED: the cycle covers exactly one direction word (RPW == mv-1, entered with o.sh == 0).
 template <int KC, int KG, int DEG, int MV, bool SHORT, bool BAND, bool ALIGNED, int PH = 0>
 __device__ __forceinline__ void dp_rows_cycle(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
-                                              const double (&xv)[MV - 1], double *__restrict__ Qlane,
-                                              const double *__restrict__ Qbase, DirOut &o) {
+                                              double (&xv)[MV - 1], const double *__restrict__ xnext,
+                                              double *__restrict__ Qlane, const double *__restrict__ Qbase,
+                                              DirOut &o) {
     constexpr int QL = q_row_len<KG>();
     constexpr int RPW = DirFmt<KC, KG, DEG>::RPW;
     constexpr int SUB = RPW == 1 ? 0 : (ALIGNED ? PH : -1);
     dp_row<KC, KG, DEG, MV, SHORT, BAND, PH, SUB>(s, lc, xv[PH], Qlane + PH * QL, Qbase + PH * QL, o);
+    xv[PH] = xnext[PH];   // the same phase's sample of the next cycle, a whole cycle ahead of its use
     if constexpr (PH + 1 < MV - 1)
-        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, ALIGNED, PH + 1>(s, lc, xv, Qlane, Qbase, o);
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, ALIGNED, PH + 1>(s, lc, xv, xnext, Qlane, Qbase, o);
 }
 
 // a single row from phase 0 back to phase 0 (registers rotated by hand; used for the few rows
@@ -282,17 +289,12 @@ __device__ __forceinline__ void dp_segment(LaneState<KC + KG, MV> &s, const Lane
             xp += 1;
         }
     }
-    double xv[CY], xn[CY];
+    double xv[CY];
 #pragma unroll
-    for (int j = 0; j < CY; ++j) xn[j] = xp[j];          // may run a few samples past the tile: unused then
+    for (int j = 0; j < CY; ++j) xv[j] = xp[j];          // may run a few samples past the tile: unused then
 #pragma unroll 1
     for (; i0 + CY <= i1; i0 += CY) {
-#pragma unroll
-        for (int j = 0; j < CY; ++j) {
-            xv[j] = xn[j];
-            xn[j] = xp[CY + j];                          // next cycle's samples, ahead of the barriers
-        }
-        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, ALIGNED>(s, lc, xv, Qlane, Qbase, o);
+        dp_rows_cycle<KC, KG, DEG, MV, SHORT, BAND, ALIGNED>(s, lc, xv, xp + CY, Qlane, Qbase, o);
         xp += CY;
     }
 #pragma unroll 1
@@ -348,9 +350,8 @@ __device__ __forceinline__ void dp_tile_rows(LaneState<KC + KG, MV> &s, const La
 // list order) visits the same cells.
 //
 // Done by the warp that filled the read, right after the fill.  The direction words are
-// staged through shared memory in windows of WRW word rows (one bulk async copy per word row
-// into a padded slot, a ring of NBUF windows in flight), so the walk never waits on HBM for
-// a dependent step.  Inside a window lane t looks at row hi-t: every lane extracts the code
+// staged through shared memory in windows of WRW word rows (one bulk async copy each, a ring
+// of NBUF windows in flight), so the walk never waits on HBM for a dependent step.  Inside a window lane t looks at row hi-t: every lane extracts the code
 // of the path's current state in its own row, one ballot finds the first row that is not a
 // "stay", all rows above it are emitted at once, and only the state changes (one per ~9
 // samples) cost a dependent step.  The trace is written one window at a time.
@@ -359,23 +360,14 @@ template <int RPW>
 struct TbGeom {
     static constexpr int WRW = RPW == 1 ? 16 : 32 / RPW;   // word rows per window (<= 32 DP rows)
     static constexpr int ROWS = WRW * RPW;                 // DP rows per window
-    static constexpr int STRIDE = 36;                      // words per padded slot (16-byte granules, spreads banks)
-    static constexpr int NBUF = RPW >= 3 ? 5 : 4;          // windows in flight
-    static constexpr int WORDS = NBUF * WRW * STRIDE;
+    static constexpr int NBUF = 5;                         // windows in flight
+    static constexpr int WORDS = NBUF * WRW * 32;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
 template <int KC, int KG, int DEG>
 __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int T, const uint32_t *dir,
                                                const uint32_t *mw, int32_t *tr, int32_t *status_slot,
@@ -383,24 +375,26 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
     constexpr int K = KC + KG;
     constexpr int NB = DirFmt<KC, KG, DEG>::NB, RPW = DirFmt<KC, KG, DEG>::RPW;
     using G = TbGeom<RPW>;
-    constexpr int WRW = G::WRW, ROWS = G::ROWS, ST = G::STRIDE, NBUF = G::NBUF;
+    constexpr int WRW = G::WRW, ROWS = G::ROWS, NBUF = G::NBUF;
     const int mv = A->mv;
     const int32_t *pred = A->pred_tab;
     const int wtop = (T - 1) / RPW;                  // last word row
     const int wmin = mv / RPW;                       // first word row that was written
     const int nwin = wtop / WRW + 1;
 
-    // window c holds word rows wh-WRW+1 .. wh, wh = wtop - c*WRW; slot s of its buffer = word row wh-s
+    // window c holds word rows wh-WRW+1 .. wh (wh = wtop - c*WRW) in memory order: one bulk copy
     auto issue = [&](int c) {
+        if (lane != 0) return;
         const int b = c % NBUF;
         const int wh = wtop - c * WRW;
-        int n = wh - wmin + 1;
-        n = n > WRW ? WRW : (n < 0 ? 0 : n);
-        if (lane == 0) mbar_expect_tx(&bar[b], static_cast<uint32_t>(n) * 128u);
-        __syncwarp();
-        const int wr = wh - lane;
-        if (lane < WRW && wr >= wmin)
-            bulk_copy(win + (b * WRW + lane) * ST, dir + static_cast<int64_t>(wr) * 32, 128u, &bar[b]);
+        const int wfirst = wh - WRW + 1;
+        const int w0 = wfirst > wmin ? wfirst : wmin;      // word rows below wmin were never written
+        const int n = wh - w0 + 1;
+        if (n > 0)
+            bulk_load(win + (b * WRW + (w0 - wfirst)) * 32, dir + static_cast<int64_t>(w0) * 32,
+                      static_cast<uint32_t>(n) * 128u, &bar[b]);
+        else
+            mbar_expect_tx(&bar[b], 0u);
     };
 
     int i = T - 1;
@@ -423,7 +417,7 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
             uint32_t mb = 0u;
             if (mw && mine && row < T) mb = (__ldg(mw + (row >> 5)) >> (row & 31)) & 1u;
             const int wr = mine ? row / RPW : wh;
-            const uint32_t *wslot = win + (b * WRW + (wh - wr)) * ST;
+            const uint32_t *wslot = win + (b * WRW + (wr - (wh - WRW + 1))) * 32;
             const int fsh = (row - wr * RPW) * NB;      // this row's bit field inside its word
             int my = -1;
             for (;;) {
