@@ -98,6 +98,7 @@ class CallerEngine:
         self.tables: List[dict] = []
         self._ws = None
         self._copy_stream = None
+        self.timeline = None      # set to a list to collect (label, CUDA event) pairs from call_arrays
         self._host_out = None
 
     # -- automata ------------------------------------------------------------------------
@@ -230,9 +231,9 @@ class CallerEngine:
                     chunk_reads: int = 25000) -> Dict[str, np.ndarray]:
         """Array-level end-to-end call: (pinned) host signal buffer in, host arrays out --
         len1 ('orig'), len2 ('results'), cost1, cost2, status and, optionally, the decoded
-        sequence bytes.  The batch is cut into chunks of ``chunk_reads`` reads; a copy stream
-        moves chunk i+1 to the device and chunk i-1's results back while the compute stream
-        works on chunk i.  ``call_batch`` wraps this into ``CallerResult`` objects."""
+        sequence bytes.  The batch is cut into chunks of ``chunk_reads`` reads; one copy stream
+        moves chunk i+1 to the device and another brings chunk i-1's results back while the
+        compute stream works on chunk i.  ``call_batch`` wraps this into ``CallerResult`` objects."""
         import torch
         n = len(lengths)
         lengths = np.asarray(lengths, dtype=np.int32)
@@ -247,37 +248,60 @@ class CallerEngine:
         with torch.cuda.device(self.device):
             comp = torch.cuda.current_stream()
             if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream()
-            cs = self._copy_stream
+                self._copy_stream = (torch.cuda.Stream(), torch.cuda.Stream())
+            cs_in, cs_out = self._copy_stream
             total = int(off[-1] + ((int(lengths[-1]) + 1) & ~1) + 2) if n else 0
             d_sig = torch.empty(min(total, host_signal.numel()), dtype=torch.float64, device=self.device)
-            cs.wait_stream(comp)
-            ready = []
-            for a, b in zip(bounds[:-1], bounds[1:]):          # all H2D copies, in order, on the copy stream
+            cs_in.wait_stream(comp)
+            cs_out.wait_stream(comp)
+            chunks = list(zip(bounds[:-1], bounds[1:]))
+
+            def mark(label, stream):
+                if self.timeline is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(stream)
+                    self.timeline.append((label, e))
+
+            mark('start', comp)
+
+            def send(a, b):                                     # chunk [a, b) -> device, on the input stream
                 lo = int(off[a])
                 hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel())
-                with torch.cuda.stream(cs):
+                with torch.cuda.stream(cs_in):
+                    mark(f'h2d{a} begin', cs_in)
                     d_sig[lo:hi].copy_(host_signal[lo:hi], non_blocking=True)
+                    mark(f'h2d{a} end', cs_in)
                     ev = torch.cuda.Event()
-                    ev.record(cs)
-                ready.append((lo, hi, ev))
+                    ev.record(cs_in)
+                return lo, hi, ev
+
             keep = []
-            for (a, b), (lo, hi, ev) in zip(zip(bounds[:-1], bounds[1:]), ready):
+            nxt = send(*chunks[0]) if chunks else None
+            for ci, (a, b) in enumerate(chunks):
+                lo, hi, ev = nxt
                 comp.wait_event(ev)
+                mark(f'call{a} begin', comp)
                 o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b], want_seq=want_seq)
+                mark(f'call{a} end', comp)
+                # the call stages its own metadata through a kernel, so the DMA engine is free for the
+                # next chunk's signal while this one computes
+                if ci + 1 < len(chunks):
+                    nxt = send(*chunks[ci + 1])
                 done = torch.cuda.Event()
                 done.record(comp)
-                with torch.cuda.stream(cs):                     # results back while the next chunk computes
-                    cs.wait_event(done)
+                with torch.cuda.stream(cs_out):                 # results back while the next chunk computes
+                    cs_out.wait_event(done)
                     for k in ('len1', 'len2', 'cost1', 'cost2', 'status'):
                         out[k][a:b].copy_(o[k], non_blocking=True)
                     if want_seq:
                         s0, s1 = int(seq_off[a]), int(seq_off[b])
                         out['seq1'][s0:s1].copy_(o['seq1'][:s1 - s0], non_blocking=True)
                         out['seq2'][s0:s1].copy_(o['seq2'][:s1 - s0], non_blocking=True)
+                    mark(f'd2h{a} end', cs_out)
                 keep.append(o)
-            cs.synchronize()
-            comp.wait_stream(cs)
+            cs_out.synchronize()
+            comp.wait_stream(cs_in)
+            comp.wait_stream(cs_out)
         res = {k: out[k][:n].numpy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
         if want_seq:
             res['seq1'] = out['seq1'][:int(seq_off[-1])].numpy()

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -445,33 +446,230 @@ extern "C" int wstr_automaton_layout(const wstr_automaton *a, int32_t *state_of_
 }
 
 // ------------------------------------------------------------------------------------------
-// DP passes over a batch, in waves that fit the workspace
+// Host plan of a batch.  Everything the kernels need to know about the reads (automaton
+// tables, per-read records, the longest-first processing order, the waves that fit the
+// direction-code workspace) is laid out once per call in a pinned, device-mapped staging slot
+// and brought into the workspace by a small copy kernel on the caller's stream -- not by the
+// DMA engines, which a pipelining caller keeps busy with the next chunk's signal.  Nothing
+// else crosses PCIe during the call and the host never waits for the device.
 // ------------------------------------------------------------------------------------------
 namespace {
 
-struct WsPlan {
-    size_t o_queue, o_auts, o_meta, o_order, o_dir, fixed_end;
+struct StageSlot {
+    void *h = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
 };
+constexpr int kStageSlots = 4;
+StageSlot g_stage[kStageSlots];
+int g_stage_next = 0;
+std::mutex g_stage_mu;
 
-WsPlan plan_workspace(int n_automata, int n_reads) {
-    WsPlan w;
-    size_t off = 0;
-    w.o_queue = off;
-    off = align_up(off + 64 * sizeof(int32_t), 256);
-    w.o_auts = off;
-    off = align_up(off + sizeof(DevAutomaton) * (size_t)n_automata, 256);
-    w.o_meta = off;
-    off = align_up(off + sizeof(ReadMeta) * (size_t)n_reads, 256);
-    w.o_order = off;
-    off = align_up(off + sizeof(int32_t) * (size_t)n_reads, 256);
-    w.o_dir = off;
-    w.fixed_end = off;
-    return w;
+// a staging slot of at least `bytes`, free to overwrite
+int stage_acquire(size_t bytes, StageSlot **out) {
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    StageSlot &sl = g_stage[g_stage_next];
+    g_stage_next = (g_stage_next + 1) % kStageSlots;
+    if (sl.pending) {
+        WSTR_CUDA(cudaEventSynchronize(sl.done));
+        sl.pending = false;
+    }
+    if (sl.cap < bytes) {
+        if (sl.h) cudaFreeHost(sl.h);
+        sl.h = nullptr;
+        sl.cap = 0;
+        const size_t cap = align_up(bytes + bytes / 4 + 4096, 4096);
+        WSTR_CUDA(cudaHostAlloc(&sl.h, cap, cudaHostAllocMapped | cudaHostAllocPortable));
+        sl.cap = cap;
+    }
+    if (!sl.done) WSTR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    *out = &sl;
+    return WSTR_OK;
 }
 
-// direction words of one read: RPW rows share a word per lane (dtw.cu: DirFmt)
-inline int64_t dir_words(const wstr_automaton *a, int T) {
+__global__ void upload_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// staged bytes -> device, on the stream; the slot is reusable once `done` has passed
+int stage_upload(StageSlot *sl, void *d_dst, size_t bytes, cudaStream_t s) {
+    const size_t n16 = (bytes + 15) / 16;
+    const int grid = (int)std::min<size_t>((n16 + 255) / 256, 512);
+    void *d_src = nullptr;
+    WSTR_CUDA(cudaHostGetDevicePointer(&d_src, sl->h, 0));
+    upload_kernel<<<grid, 256, 0, s>>>(static_cast<uint4 *>(d_dst), static_cast<const uint4 *>(d_src), n16);
+    WSTR_CUDA(cudaGetLastError());
+    WSTR_CUDA(cudaEventRecord(sl->done, s));
+    sl->pending = true;
+    return WSTR_OK;
+}
+
+inline int64_t dir_words(const wstr_automaton *a, int T) {   // RPW rows share a word per lane (dtw.cu: DirFmt)
     return ((int64_t)T + a->dev.RPW - 1) / a->dev.RPW * 32;
+}
+
+struct FillLaunch {
+    int kc, kg, deg;
+    int begin, n;      // slice of the order array
+    int counter;       // index of its work counter
+};
+struct Wave {
+    std::vector<FillLaunch> launches;
+};
+
+// block uploaded per call: [DevAutomaton x A][ReadMeta x n][order x n] (+ the mid-stage tables)
+struct BlockLayout {
+    size_t o_auts, o_meta, o_order, o_mauts, o_reads, bytes;
+};
+BlockLayout block_layout(int n_automata, int n_reads, bool with_mid) {
+    BlockLayout b;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    b.o_auts = take(sizeof(DevAutomaton) * (size_t)n_automata);
+    b.o_meta = take(sizeof(ReadMeta) * (size_t)n_reads);
+    b.o_order = take(sizeof(int32_t) * (size_t)n_reads);
+    b.o_mauts = take(with_mid ? sizeof(MidAutomaton) * (size_t)n_automata : 0);
+    b.o_reads = take(with_mid ? sizeof(MidRead) * (size_t)n_reads : 0);
+    b.bytes = off;
+    return b;
+}
+
+constexpr int kCounters = 64;   // work counters per wave (one per kernel shape present)
+
+// Fill the DP part of the block and cut the batch into waves.  mask_off may be NULL.
+int plan_fill(wstr_automaton *const *automata, int n_automata, const int32_t *read_automaton, const int64_t *sig_off,
+              const int32_t *lengths, const int64_t *mask_off, int n_reads, int64_t dir_capacity,
+              unsigned char *block, const BlockLayout &bl, std::vector<Wave> &waves) {
+    DevAutomaton *h_auts = reinterpret_cast<DevAutomaton *>(block + bl.o_auts);
+    ReadMeta *meta = reinterpret_cast<ReadMeta *>(block + bl.o_meta);
+    int32_t *order = reinterpret_cast<int32_t *>(block + bl.o_order);
+    for (int a = 0; a < n_automata; ++a) h_auts[a] = automata[a]->dev;
+
+    // longest reads first
+    std::vector<int> idx(n_reads);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lengths[x] > lengths[y]; });
+
+    waves.clear();
+    int cursor = 0;
+    std::vector<char> done;
+    while (cursor < n_reads) {
+        const int wave_begin = cursor;
+        int64_t used = 0;
+        while (cursor < n_reads) {
+            const int r = idx[cursor];
+            const int a = read_automaton ? read_automaton[r] : 0;
+            const int64_t need = dir_words(automata[a], lengths[r]);
+            if (used + need > dir_capacity) break;
+            ReadMeta &m = meta[cursor];
+            m.sig_off = sig_off[r];
+            m.dir_off = used;
+            m.mask_off = mask_off ? mask_off[r] : 0;
+            m.T = lengths[r];
+            m.aut = a;
+            m.read = r;
+            m.pad_ = 0;
+            used += need;
+            ++cursor;
+        }
+        if (cursor == wave_begin) return WSTR_ERR_WORKSPACE_TOO_SMALL;   // one read does not fit
+        // one launch per kernel shape (chain slots, generic slots, in-degree) present in this wave
+        Wave w;
+        const int nw = cursor - wave_begin;
+        done.assign(nw, 0);
+        int filled = wave_begin;
+        for (int i0 = 0; i0 < nw; ++i0) {
+            if (done[i0]) continue;
+            const DevAutomaton &ref = automata[meta[wave_begin + i0].aut]->dev;
+            FillLaunch fl;
+            fl.kc = ref.KC;
+            fl.kg = ref.KG;
+            fl.deg = ref.DEG;
+            fl.begin = filled;
+            for (int i = i0; i < nw; ++i) {
+                const DevAutomaton &o = automata[meta[wave_begin + i].aut]->dev;
+                if (!done[i] && o.KC == ref.KC && o.KG == ref.KG && o.DEG == ref.DEG) {
+                    order[filled++] = wave_begin + i;
+                    done[i] = 1;
+                }
+            }
+            fl.n = filled - fl.begin;
+            fl.counter = (int)w.launches.size();
+            if (fl.counter >= kCounters) return WSTR_ERR_UNSUPPORTED;
+            w.launches.push_back(fl);
+        }
+        waves.push_back(std::move(w));
+    }
+    return WSTR_OK;
+}
+
+struct FillDevice {
+    const DevAutomaton *auts;
+    const ReadMeta *meta;
+    const int32_t *order;
+    int32_t *counters;    // kCounters ints
+    uint32_t *dir;
+};
+
+// one DP pass (fill + traceback) over the planned waves; no host<->device traffic
+int run_fill(const std::vector<Wave> &waves, const FillDevice &fd, int mv, const double *d_signal,
+             const uint32_t *d_maskbits, int32_t *d_trace, double *d_end_cost, int32_t *d_status, int respect_status,
+             cudaStream_t s) {
+    for (const Wave &w : waves) {
+        WSTR_CUDA(cudaMemsetAsync(fd.counters, 0, kCounters * sizeof(int32_t), s));
+        for (const FillLaunch &fl : w.launches) {
+            FillParams fp;
+            fp.auts = fd.auts;
+            fp.meta = fd.meta;
+            fp.order = fd.order + fl.begin;
+            fp.n = fl.n;
+            fp.queue = fd.counters + fl.counter;
+            fp.signal = d_signal;
+            fp.maskbits = d_maskbits;
+            fp.dir = fd.dir;
+            fp.trace = d_trace;
+            fp.end_cost = d_end_cost;
+            fp.status = d_status;
+            fp.respect_status = respect_status;
+            wstr_prof_begin(0, s);
+            const int rc = wstr_launch_fill(fl.kc, fl.kg, fl.deg, mv, fp, s);
+            wstr_prof_end(s);
+            if (rc != WSTR_OK) return rc;
+        }
+    }
+    return WSTR_OK;
+}
+
+int check_reads(wstr_automaton *const *automata, int n_automata, const int32_t *read_automaton, const int64_t *sig_off,
+                const int32_t *lengths, int n_reads) {
+    const int mv = automata[0]->dev.mv;
+    for (int a = 0; a < n_automata; ++a)
+        if (!automata[a] || automata[a]->dev.mv != mv) return WSTR_ERR_INVALID_ARGUMENT;
+    for (int r = 0; r < n_reads; ++r) {
+        const int a = read_automaton ? read_automaton[r] : 0;
+        if (a < 0 || a >= n_automata || lengths[r] < 0 || (sig_off[r] & 1)) return WSTR_ERR_INVALID_ARGUMENT;
+    }
+    return WSTR_OK;
+}
+
+// workspace of a stand-alone pass: [counters][block][direction codes]
+struct WarpWs {
+    size_t o_counters, o_block, o_dir;
+    BlockLayout bl;
+};
+WarpWs plan_warp_ws(int n_automata, int n_reads) {
+    WarpWs w;
+    w.bl = block_layout(n_automata, n_reads, false);
+    w.o_counters = 0;
+    w.o_block = 256;
+    w.o_dir = align_up(w.o_block + w.bl.bytes, 256);
+    return w;
 }
 
 }  // namespace
@@ -480,126 +678,14 @@ extern "C" int64_t wstr_warp_workspace_bytes(wstr_automaton *const *automata, in
                                              const int32_t *read_automaton, const int32_t *lengths,
                                              int32_t n_reads) {
     if (!automata || n_automata <= 0 || n_reads < 0) return WSTR_ERR_INVALID_ARGUMENT;
-    WsPlan w = plan_workspace(n_automata, n_reads);
+    const WarpWs w = plan_warp_ws(n_automata, n_reads);
     int64_t words = 0;
     for (int r = 0; r < n_reads; ++r) {
         const int a = read_automaton ? read_automaton[r] : 0;
         if (a < 0 || a >= n_automata) return WSTR_ERR_INVALID_ARGUMENT;
         words += dir_words(automata[a], lengths[r]);
     }
-    return (int64_t)w.fixed_end + words * 4 + 256;
-}
-
-static int warp_pass(wstr_automaton *const *automata, int32_t n_automata, const int32_t *read_automaton,
-                     const double *d_signal, const int64_t *sig_off, const int32_t *lengths,
-                     const uint32_t *d_maskbits, const int64_t *mask_off, int32_t n_reads, void *d_workspace,
-                     int64_t workspace_bytes, int32_t *d_trace, double *d_end_cost, int32_t *d_status,
-                     void *stream, int respect_status) {
-    if (!automata || n_automata <= 0 || n_reads < 0 || !d_signal || !sig_off || !lengths || !d_workspace ||
-        !d_trace || !d_status)
-        return WSTR_ERR_INVALID_ARGUMENT;
-    if (d_maskbits && !mask_off) return WSTR_ERR_INVALID_ARGUMENT;
-    if (n_reads == 0) return WSTR_OK;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int mv = automata[0]->dev.mv;
-    for (int a = 0; a < n_automata; ++a)
-        if (!automata[a] || automata[a]->dev.mv != mv) return WSTR_ERR_INVALID_ARGUMENT;
-    for (int r = 0; r < n_reads; ++r) {
-        const int a = read_automaton ? read_automaton[r] : 0;
-        if (a < 0 || a >= n_automata || lengths[r] < 0 || (sig_off[r] & 1)) return WSTR_ERR_INVALID_ARGUMENT;
-    }
-
-    const WsPlan w = plan_workspace(n_automata, n_reads);
-    if ((int64_t)w.fixed_end >= workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
-    const int64_t dir_capacity = (workspace_bytes - (int64_t)w.o_dir) / 4;
-    unsigned char *ws = static_cast<unsigned char *>(d_workspace);
-    int32_t *d_queue = reinterpret_cast<int32_t *>(ws + w.o_queue);
-    DevAutomaton *d_auts = reinterpret_cast<DevAutomaton *>(ws + w.o_auts);
-    ReadMeta *d_meta = reinterpret_cast<ReadMeta *>(ws + w.o_meta);
-    int32_t *d_order = reinterpret_cast<int32_t *>(ws + w.o_order);
-    uint32_t *d_dir = reinterpret_cast<uint32_t *>(ws + w.o_dir);
-
-    std::vector<DevAutomaton> h_auts(n_automata);
-    for (int a = 0; a < n_automata; ++a) h_auts[a] = automata[a]->dev;
-    WSTR_CUDA(cudaMemcpyAsync(d_auts, h_auts.data(), sizeof(DevAutomaton) * n_automata, cudaMemcpyHostToDevice, s));
-
-    // longest reads first, grouped by automaton so that a warp rarely reloads its tables
-    std::vector<int> idx(n_reads);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lengths[x] > lengths[y]; });
-
-    std::vector<ReadMeta> meta;
-    std::vector<int32_t> order;
-    size_t cursor = 0;
-    while (cursor < (size_t)n_reads) {
-        meta.clear();
-        int64_t used = 0;
-        while (cursor < (size_t)n_reads) {
-            const int r = idx[cursor];
-            const int a = read_automaton ? read_automaton[r] : 0;
-            const int64_t need = dir_words(automata[a], lengths[r]);
-            if (used + need > dir_capacity) break;
-            ReadMeta m;
-            m.sig_off = sig_off[r];
-            m.dir_off = used;
-            m.mask_off = mask_off ? mask_off[r] : 0;
-            m.T = lengths[r];
-            m.aut = a;
-            m.read = r;
-            m.pad_ = 0;
-            meta.push_back(m);
-            used += need;
-            ++cursor;
-        }
-        if (meta.empty()) return WSTR_ERR_WORKSPACE_TOO_SMALL;   // one read does not fit
-        const int nw = (int)meta.size();
-        WSTR_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(ReadMeta) * nw, cudaMemcpyHostToDevice, s));
-        WSTR_CUDA(cudaMemsetAsync(d_queue, 0, 64 * sizeof(int32_t), s));
-
-        // one launch per kernel shape (chain slots, generic slots, in-degree) present in this wave
-        order.assign(nw, 0);
-        int filled = 0, cls = 0;
-        std::vector<char> done(nw, 0);
-        for (int i0 = 0; i0 < nw; ++i0) {
-            if (done[i0]) continue;
-            const DevAutomaton &ref = automata[meta[i0].aut]->dev;
-            const int begin = filled;
-            for (int i = i0; i < nw; ++i) {
-                const DevAutomaton &o = automata[meta[i].aut]->dev;
-                if (!done[i] && o.KC == ref.KC && o.KG == ref.KG && o.DEG == ref.DEG) {
-                    order[filled++] = i;
-                    done[i] = 1;
-                }
-            }
-            if (cls >= 64) return WSTR_ERR_UNSUPPORTED;
-            WSTR_CUDA(cudaMemcpyAsync(d_order + begin, order.data() + begin, sizeof(int32_t) * (filled - begin),
-                                      cudaMemcpyHostToDevice, s));
-            FillParams fp;
-            fp.auts = d_auts;
-            fp.meta = d_meta;
-            fp.order = d_order + begin;
-            fp.n = filled - begin;
-            fp.queue = d_queue + cls;
-            fp.signal = d_signal;
-            fp.maskbits = d_maskbits;
-            fp.dir = d_dir;
-            fp.trace = d_trace;
-            fp.end_cost = d_end_cost;
-            fp.status = d_status;
-            fp.respect_status = respect_status;
-            wstr_prof_begin(0, s);
-            int rc = wstr_launch_fill(ref.KC, ref.KG, ref.DEG, mv, fp, s);
-            wstr_prof_end(s);
-            if (rc != WSTR_OK) return rc;
-            ++cls;
-        }
-        if (cursor < (size_t)n_reads) {
-            // the next wave overwrites meta/order staging on the host side; the device copies are
-            // stream-ordered, but the pageable source vectors are reused, so drain first
-            WSTR_CUDA(cudaStreamSynchronize(s));
-        }
-    }
-    return WSTR_OK;
+    return (int64_t)w.o_dir + words * 4 + 256;
 }
 
 extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automata,
@@ -607,8 +693,35 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
                                const int32_t *lengths, const uint32_t *d_maskbits, const int64_t *mask_off,
                                int32_t n_reads, void *d_workspace, int64_t workspace_bytes, int32_t *d_trace,
                                double *d_end_cost, int32_t *d_status, void *stream) {
-    return warp_pass(automata, n_automata, read_automaton, d_signal, sig_off, lengths, d_maskbits, mask_off,
-                     n_reads, d_workspace, workspace_bytes, d_trace, d_end_cost, d_status, stream, 0);
+    if (!automata || n_automata <= 0 || n_reads < 0 || !d_signal || !sig_off || !lengths || !d_workspace ||
+        !d_trace || !d_status)
+        return WSTR_ERR_INVALID_ARGUMENT;
+    if (d_maskbits && !mask_off) return WSTR_ERR_INVALID_ARGUMENT;
+    if (n_reads == 0) return WSTR_OK;
+    int rc = check_reads(automata, n_automata, read_automaton, sig_off, lengths, n_reads);
+    if (rc != WSTR_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const WarpWs w = plan_warp_ws(n_automata, n_reads);
+    if ((int64_t)w.o_dir >= workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    unsigned char *ws = static_cast<unsigned char *>(d_workspace);
+
+    StageSlot *slot = nullptr;
+    rc = stage_acquire(w.bl.bytes, &slot);
+    if (rc != WSTR_OK) return rc;
+    std::vector<Wave> waves;
+    rc = plan_fill(automata, n_automata, read_automaton, sig_off, lengths, d_maskbits ? mask_off : nullptr, n_reads,
+                   (workspace_bytes - (int64_t)w.o_dir) / 4, static_cast<unsigned char *>(slot->h), w.bl, waves);
+    if (rc != WSTR_OK) return rc;
+    rc = stage_upload(slot, ws + w.o_block, w.bl.bytes, s);
+    if (rc != WSTR_OK) return rc;
+
+    FillDevice fd;
+    fd.auts = reinterpret_cast<const DevAutomaton *>(ws + w.o_block + w.bl.o_auts);
+    fd.meta = reinterpret_cast<const ReadMeta *>(ws + w.o_block + w.bl.o_meta);
+    fd.order = reinterpret_cast<const int32_t *>(ws + w.o_block + w.bl.o_order);
+    fd.counters = reinterpret_cast<int32_t *>(ws + w.o_counters);
+    fd.dir = reinterpret_cast<uint32_t *>(ws + w.o_dir);
+    return run_fill(waves, fd, automata[0]->dev.mv, d_signal, d_maskbits, d_trace, d_end_cost, d_status, 0, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -617,7 +730,8 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
 namespace {
 
 struct CallPlan {
-    size_t o_queue, o_mauts, o_reads, o_state, o_cubic, o_resc, o_trace, o_mask, o_scratch, o_warp;
+    size_t o_counters, o_queue, o_block, o_state, o_cubic, o_resc, o_trace, o_mask, o_scratch, o_dir;
+    BlockLayout bl;
     int64_t extent;       // elements of the signal buffer in use
     int64_t mask_words;
     int64_t scratch_bytes;
@@ -637,22 +751,23 @@ CallPlan plan_call(int n_automata, int n_reads, const int64_t *sig_off, const in
         c.mask_words += (lengths[r] + 31) / 32;
         c.scratch_bytes += wstr_mid_scratch_bytes(lengths[r], mv);
     }
+    c.bl = block_layout(n_automata, n_reads, true);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
         off = align_up(off + bytes, 256);
         return o;
     };
+    c.o_counters = take(kCounters * sizeof(int32_t));
     c.o_queue = take(256);
-    c.o_mauts = take(sizeof(MidAutomaton) * (size_t)n_automata);
-    c.o_reads = take(sizeof(MidRead) * (size_t)n_reads);
+    c.o_block = take(c.bl.bytes);
     c.o_state = take(sizeof(MidState) * (size_t)n_reads);
     c.o_cubic = take(sizeof(double) * 8 * (size_t)n_reads);
     c.o_resc = take(own_resc ? sizeof(double) * (size_t)c.extent : 0);
     c.o_trace = take(own_trace ? sizeof(int32_t) * (size_t)c.extent : 0);
     c.o_mask = take(sizeof(uint32_t) * (size_t)(c.mask_words + 1));
     c.o_scratch = take((size_t)c.scratch_bytes);
-    c.o_warp = off;
+    c.o_dir = off;
     return c;
 }
 
@@ -662,10 +777,14 @@ extern "C" int64_t wstr_call_workspace_bytes(wstr_automaton *const *automata, in
                                              const int32_t *read_automaton, const int32_t *lengths,
                                              int32_t n_reads) {
     if (!automata || n_automata <= 0 || n_reads < 0 || !lengths) return WSTR_ERR_INVALID_ARGUMENT;
-    const int64_t warp = wstr_warp_workspace_bytes(automata, n_automata, read_automaton, lengths, n_reads);
-    if (warp < 0) return warp;
+    int64_t words = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        const int a = read_automaton ? read_automaton[r] : 0;
+        if (a < 0 || a >= n_automata) return WSTR_ERR_INVALID_ARGUMENT;
+        words += dir_words(automata[a], lengths[r]);
+    }
     const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true);
-    return (int64_t)c.o_warp + warp;
+    return (int64_t)c.o_dir + words * 4 + 256;
 }
 
 extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,
@@ -682,19 +801,16 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     if (params->states_in_segment < 2) return WSTR_ERR_INVALID_ARGUMENT;
     const int mv = automata[0]->dev.mv;
     if (params->min_values_per_state != mv) return WSTR_ERR_INVALID_ARGUMENT;
-    for (int r = 0; r < n_reads; ++r) {
-        const int a = read_automaton ? read_automaton[r] : 0;
-        if (a < 0 || a >= n_automata || lengths[r] < 0 || (sig_off[r] & 1)) return WSTR_ERR_INVALID_ARGUMENT;
-    }
+    int rc = check_reads(automata, n_automata, read_automaton, sig_off, lengths, n_reads);
+    if (rc != WSTR_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool own_resc = out->d_rescaled == nullptr;
     const bool own_trace = out->d_trace1 == nullptr || out->d_trace2 == nullptr;
     const CallPlan c = plan_call(n_automata, n_reads, sig_off, lengths, mv, own_resc, own_trace);
-    if ((int64_t)c.o_warp >= workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    if ((int64_t)c.o_dir >= workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
     unsigned char *ws = static_cast<unsigned char *>(d_workspace);
+    unsigned char *d_block = ws + c.o_block;
     int32_t *d_queue = reinterpret_cast<int32_t *>(ws + c.o_queue);
-    MidAutomaton *d_mauts = reinterpret_cast<MidAutomaton *>(ws + c.o_mauts);
-    MidRead *d_reads = reinterpret_cast<MidRead *>(ws + c.o_reads);
     MidState *d_state = reinterpret_cast<MidState *>(ws + c.o_state);
     double *d_cubic = reinterpret_cast<double *>(ws + c.o_cubic);
     double *d_resc = own_resc ? reinterpret_cast<double *>(ws + c.o_resc) : out->d_rescaled;
@@ -703,10 +819,13 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     int32_t *d_trace2 = out->d_trace2 ? out->d_trace2 : d_own_trace;
     uint32_t *d_mask = reinterpret_cast<uint32_t *>(ws + c.o_mask);
     unsigned char *d_scratch = ws + c.o_scratch;
-    void *warp_ws = ws + c.o_warp;
-    const int64_t warp_bytes = workspace_bytes - (int64_t)c.o_warp;
 
-    std::vector<MidAutomaton> mauts(n_automata);
+    // ---- the whole host plan, staged and uploaded in one piece -----------------------------
+    StageSlot *slot = nullptr;
+    rc = stage_acquire(c.bl.bytes, &slot);
+    if (rc != WSTR_OK) return rc;
+    unsigned char *block = static_cast<unsigned char *>(slot->h);
+    MidAutomaton *mauts = reinterpret_cast<MidAutomaton *>(block + c.bl.o_mauts);
     for (int a = 0; a < n_automata; ++a) {
         mauts[a].values = automata[a]->d_values;
         mauts[a].seq_idx = automata[a]->d_seq_idx;
@@ -715,7 +834,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
         mauts[a].flank_length = automata[a]->flank_length;
         mauts[a].pad_ = 0;
     }
-    std::vector<MidRead> reads(n_reads);
+    MidRead *reads = reinterpret_cast<MidRead *>(block + c.bl.o_reads);
     std::vector<int64_t> mask_off(n_reads);
     int64_t mo = 0, so = 0;
     for (int r = 0; r < n_reads; ++r) {
@@ -734,16 +853,26 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
         mo += (lengths[r] + 31) / 32;
         so += wstr_mid_scratch_bytes(lengths[r], mv);
     }
-    WSTR_CUDA(cudaMemcpyAsync(d_mauts, mauts.data(), sizeof(MidAutomaton) * n_automata, cudaMemcpyHostToDevice, s));
-    WSTR_CUDA(cudaMemcpyAsync(d_reads, reads.data(), sizeof(MidRead) * n_reads, cudaMemcpyHostToDevice, s));
+    std::vector<Wave> waves;
+    rc = plan_fill(automata, n_automata, read_automaton, sig_off, lengths, mask_off.data(), n_reads,
+                   (workspace_bytes - (int64_t)c.o_dir) / 4, block, c.bl, waves);
+    if (rc != WSTR_OK) return rc;
+    rc = stage_upload(slot, d_block, c.bl.bytes, s);
+    if (rc != WSTR_OK) return rc;
+
+    FillDevice fd;
+    fd.auts = reinterpret_cast<const DevAutomaton *>(d_block + c.bl.o_auts);
+    fd.meta = reinterpret_cast<const ReadMeta *>(d_block + c.bl.o_meta);
+    fd.order = reinterpret_cast<const int32_t *>(d_block + c.bl.o_order);
+    fd.counters = reinterpret_cast<int32_t *>(ws + c.o_counters);
+    fd.dir = reinterpret_cast<uint32_t *>(ws + c.o_dir);
 
     // ---- first pass --------------------------------------------------------------------------
-    int rc = warp_pass(automata, n_automata, read_automaton, d_signal, sig_off, lengths, nullptr, nullptr, n_reads,
-                       warp_ws, warp_bytes, d_trace1, nullptr, out->d_status, stream, 0);
+    rc = run_fill(waves, fd, mv, d_signal, nullptr, d_trace1, nullptr, out->d_status, 0, s);
     if (rc != WSTR_OK) return rc;
     MidParams mp;
-    mp.auts = d_mauts;
-    mp.reads = d_reads;
+    mp.auts = reinterpret_cast<const MidAutomaton *>(d_block + c.bl.o_mauts);
+    mp.reads = reinterpret_cast<const MidRead *>(d_block + c.bl.o_reads);
     mp.n = n_reads;
     mp.queue = d_queue;
     mp.x = d_signal;
@@ -768,8 +897,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     if (rc != WSTR_OK) return rc;
 
     // ---- second pass on the rescaled signal, masked rows allow the shorter dwell ----------------
-    rc = warp_pass(automata, n_automata, read_automaton, d_resc, sig_off, lengths, d_mask, mask_off.data(), n_reads,
-                   warp_ws, warp_bytes, d_trace2, nullptr, out->d_status, stream, 1);
+    rc = run_fill(waves, fd, mv, d_resc, d_mask, d_trace2, nullptr, out->d_status, 1, s);
     if (rc != WSTR_OK) return rc;
     mp.x = d_resc;
     mp.trace = d_trace2;

@@ -480,7 +480,7 @@ struct alignas(16) FillSmem {
 };
 
 #ifndef WSTR_K8_BLOCKS
-#define WSTR_K8_BLOCKS 4
+#define WSTR_K8_BLOCKS 3
 #endif
 #ifdef WSTR_MAXNREG
 #define WSTR_FILL_BOUNDS __maxnreg__(WSTR_MAXNREG)
