@@ -18,6 +18,7 @@ One step = the whole per-read call (two DP passes + everything between them) ove
           host cores (multiprocessing.Pool over reads, as CallerWrapper.run does)
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -152,8 +153,9 @@ def main():
     config = {'workload': f'synthetic {args.locus} locus, {args.reads} reads per GPU, ~3.3k float64 samples/read, '
                           '50% reverse strand (BASELINE configs[1])',
               'reads_per_gpu': args.reads, 'locus': args.locus, 'flank_length': 110,
-              'cache_policy': 'inputs (2.6 GB/GPU) and traceback bits (42 GB/GPU) far exceed the 126 MB L2; no flush needed',
-              'parallelism': f'reads sharded over {args.gpus} GPU(s), no data-path collective'}
+              'cache_policy': 'inputs (2.6 GB/GPU) and direction codes (14 GB/GPU per pass) far exceed the 126 MB L2; no flush needed',
+              'parallelism': f'reads sharded over {args.gpus} GPU(s), no data-path collective; per-read results '
+                             'all_gathered (NCCL) once per step when N > 1'}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == 'reference':
@@ -228,11 +230,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from warpstr_b200 import shard
+
     def step_resident():
-        return eng.call_packed(d_sig, off, lengths, aut, rev, want_seq=True)
+        o = eng.call_packed(d_sig, off, lengths, aut, rev, want_seq=True)
+        if world > 1:   # the only exchange of the path: everybody's per-read lengths / costs / status
+            o['gathered'] = shard.gather_device(o['len1'], o['len2'], o['status'], o['cost1'], o['cost2'])
+        return o
 
     def step_e2e():
-        return eng.call_arrays(host, off, lengths, aut, rev)
+        res = eng.call_arrays(host, off, lengths, aut, rev)
+        if world > 1:
+            ints = torch.from_numpy(np.stack((res['len1'], res['len2'], res['status']), axis=1)).cuda()
+            flts = torch.from_numpy(np.stack((res['cost1'], res['cost2']), axis=1)).cuda()
+            g = shard.gather_device(ints[:, 0], ints[:, 1], ints[:, 2], flts[:, 0], flts[:, 1])
+            res['gathered_len2'] = g['len2'].cpu().numpy()
+        return res
 
     # parity spot check of the benchmark batch itself (a few reads against the oracle, rank 0)
     o = step_resident()
@@ -255,6 +268,8 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    gc.collect()
+    gc.disable()          # no collector pauses inside the timed regions
     _lib.profile_enable(True)
     _lib.profile_read()
     sampler = ClockSampler(local_rank)
@@ -271,19 +286,22 @@ def main():
     _lib.profile_enable(False)
 
     # ---- end-to-end timing (host buffers in, host arrays out) --------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    per_step = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         res = step_e2e()
+        per_step.append(round(1e3 * (time.perf_counter() - ts), 1))
     e3.record()
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
     h2d = int(host.numel() * 8)
-    d2h = int(sum(v.nbytes for v in res.values()))
+    d2h = int(sum(v.nbytes for k, v in res.items() if not k.startswith('gathered')))
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -308,6 +326,23 @@ def main():
                 traffic = tj.get('dram_bytes_per_launch_at_bench_size') * (args.reads / waves) / tj.get('reads', 100000)
             except Exception:
                 traffic = None
+        # FP64-pipe instructions the kernel executes per DP row of one read (32 lanes x 8 slots; HD layout
+        # 6 chain + 2 generic slots, in-degree 2): DADD 5 per chain slot, 6 per generic; DSETP 1 per candidate
+        fp64_per_row = 32 * ((5 * 6 + 6 * 2) + (6 + 2 * 2))
+        rows_pass = float(lengths.astype(np.int64).sum())
+        secs = fill_ms_launch * 1e-3
+        hbm_peak = None
+        ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(ppath):
+            try:
+                hbm_peak = float(json.load(open(ppath))['hbm_gbs'])
+            except Exception:
+                hbm_peak = None
+        hbm_src = 'MEASURED_PEAKS.json hbm_gbs (measured)' if hbm_peak else 'fallback 6650 GB/s (B200_PROFILING.md)'
+        hbm_peak = hbm_peak or 6650.0
+        # algorithmic HBM bytes of one pass: direction codes written once and read once by the traceback
+        # (128 B per 3 rows), signal read (8 B/row), trace written (4 B/row)
+        alg_bytes = rows_pass / waves * (2 * 128.0 / 3.0 + 8.0 + 4.0)
         line = {
             'metric': METRIC, 'value': total_reads * args.steps / (ms_total * 1e-3), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
@@ -317,18 +352,25 @@ def main():
             'dp_gcups_note': 'cells (T*S per pass) / device time of the fill+traceback kernel, all GPUs',
             'e2e': {'value': total_reads * args.steps / (ms_e2e * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'api': 'CallerEngine.call_arrays (pinned host signal -> wstr_call_batch -> host arrays)'},
-            'gpu_launches': int(fill['launches'] + 3 * (mid['launches'] // 2) + 2 * (mid['launches'] - mid['launches'] // 2)),
+                    'api': 'CallerEngine.call_arrays (pinned host signal -> wstr_call_batch -> host arrays)',
+                    'ms_each_step': per_step},
+            'gpu_launches': int(fill['launches'] + 3 * (mid['launches'] // 2) + 2 * (mid['launches'] - mid['launches'] // 2)
+                                + 2 * args.steps),
             'kernel_ms_per_step': {'dp_fill_traceback': fill['ms'] / args.steps, 'midstage': mid['ms'] / args.steps},
             'roofline': {'bound': 'fp64_add_pipe', 'achieved': achieved, 'peak': fp64_rate, 'unit': 'T FP64 add-class op/s',
                          'frac': achieved / fp64_rate, 'traffic': traffic,
                          'kernel': 'dtw_fill_kernel (fill + traceback)',
+                         'note': 'the DP is FP64 add/compare work, not HBM- or tensor-bound (SURVEY 8d); achieved = '
+                                 'algorithmic ops (4 + 5 E/S per cell) per launch / launch time; frac_executed counts '
+                                 'the FP64-pipe instructions the kernel really issues',
                          'peak_source': 'measured in this run by wstr_measure_fp64_add_rate (DADD stream on all SMs); '
                                         'MEASURED_PEAKS.json has no FP64 figure',
                          'algorithmic_ops_per_cell': alg_ops_pass / cells_pass,
-                         'executed_fp64_ops_per_cell': 6.1,
-                         'frac_executed': gcups * 1e9 * 6.1 / 1e12 / fp64_rate,
-                         'hbm_gbs_algorithmic': (cells_pass / waves) * 0.5 / (fill_ms_launch * 1e-3) / 1e9},
+                         'executed_fp64_instr_per_row': fp64_per_row,
+                         'frac_executed': rows_pass / waves * fp64_per_row / secs / 1e12 / fp64_rate,
+                         'hbm': {'bound': 'hbm', 'achieved': alg_bytes / secs / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                                 'frac': alg_bytes / secs / 1e9 / hbm_peak, 'peak_source': hbm_src,
+                                 'algorithmic_bytes_per_launch': alg_bytes}},
             'cpu_baseline': cpu_baseline,
             'clocks': clocks,
             'parity': {'reads_exact_vs_truth': exact, 'host_fallback_reads': n_fallback,

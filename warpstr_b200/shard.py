@@ -83,6 +83,21 @@ def gather_records(ids: np.ndarray, ints: np.ndarray, floats: np.ndarray, n_tota
     return dict(len1=len1, len2=len2, status=status, cost1=cost1, cost2=cost2)
 
 
+def gather_device(len1, len2, status, cost1, cost2, group=None):
+    """all_gather of equal-sized per-read device results (every rank called the same number of
+    reads): two collectives, 12 + 16 bytes per read.  Returns rank-major concatenations."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    ints = torch.stack((len1, len2, status), dim=1).contiguous()
+    flts = torch.stack((cost1, cost2), dim=1).contiguous()
+    g_i = torch.empty((world * ints.shape[0], 3), dtype=ints.dtype, device=ints.device)
+    g_f = torch.empty((world * flts.shape[0], 2), dtype=flts.dtype, device=flts.device)
+    dist.all_gather_into_tensor(g_i, ints, group=group)
+    dist.all_gather_into_tensor(g_f, flts, group=group)
+    return dict(len1=g_i[:, 0], len2=g_i[:, 1], status=g_i[:, 2], cost1=g_f[:, 0], cost2=g_f[:, 1])
+
+
 def call_sharded(engine, signals: Sequence[np.ndarray], aut_ids: Sequence[int], reverse: Sequence[bool],
                  n_states: Sequence[int], group=None) -> Dict[str, np.ndarray]:
     """Every rank holds the same read list (or at least its own shard's signals), calls its
