@@ -176,3 +176,46 @@ def test_call_arrays_pipelined_chunks_equal_single_call(engine):
             a, b = int(got['seq_off'][r]), int(one['seq_off'][r])
             n = int(got['len2'][r])
             assert np.array_equal(got['seq2'][a:a + n], s1[b:b + n])
+
+
+@pytest.mark.parametrize('name,flank_arg', [('HD', 200), ('AAAT', 160), ('DM2', 230)])
+def test_open_end_band(engine, oracle_c, name, flank_arg):
+    """flank_length larger than the real right flank puts the end band's cut inside the repeat
+    region, where back edges lead from kept states into skipped ones: the kernel must then keep
+    the per-cell band test for every banded row (DevAutomaton.band_closed == 0)."""
+    locus = synth.make_locus(name, seed=31, flank_length=110)
+    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    ids = [engine.add_automaton(s, flank_arg) for s in stas]
+    reads = synth.make_reads(locus, 5, seed=131)
+    sigs = [r.signal for r in reads]
+    aut = [ids[int(r.reverse)] for r in reads]
+    traces, costs = engine.warp_batch(sigs, aut, return_end_cost=True)
+    rng = np.random.default_rng(8)
+    masks = []
+    for r in reads:
+        m = np.zeros(len(r.signal), dtype=bool)
+        m[rng.integers(0, len(m), 200)] = True
+        m[len(m) - 700:len(m) - 500] = True          # a masked stretch across the band's first rows
+        masks.append(m)
+    traces_m = engine.warp_batch(sigs, aut, masks)
+    for r, t, c, tm, m in zip(reads, traces, costs, traces_m, masks):
+        tb = co.tables_from(stas[int(r.reverse)])
+        m0 = np.zeros(len(r.signal), dtype=bool)
+        assert np.array_equal(t, oracle_c.warp(r.signal, tb, m0, 4, flank_arg)), (name, r.name)
+        assert c == oracle_c.fill(r.signal, tb, m0, 4, flank_arg)[-1, tb.endstate]
+        assert np.array_equal(tm, oracle_c.warp(r.signal, tb, m, 4, flank_arg)), (name, r.name, 'masked')
+
+
+def test_band_starts_on_any_row_phase(engine, oracle_c):
+    """Reads whose lengths differ by one sample put the band's first row (and the last, partly
+    filled direction word) on every phase of the 3-row cycle."""
+    locus, stas, ids, reads = _setup(engine, 'HD', 2, seed=77)
+    base = reads[0]
+    sigs = [np.ascontiguousarray(base.signal[:len(base.signal) - k]) for k in range(7)]
+    aut = [ids[int(base.reverse)]] * len(sigs)
+    traces, costs = engine.warp_batch(sigs, aut, return_end_cost=True)
+    tb = co.tables_from(stas[int(base.reverse)])
+    for x, t, c in zip(sigs, traces, costs):
+        m0 = np.zeros(len(x), dtype=bool)
+        assert np.array_equal(t, oracle_c.warp(x, tb, m0, 4, 110)), len(x)
+        assert c == oracle_c.fill(x, tb, m0, 4, 110)[-1, tb.endstate]

@@ -211,22 +211,24 @@ class CallerWrapper:
 
 def get_workload(df_overview, path: str, spike_removal: str = 'Brute') -> List[ReadSignal]:
     """Reads of the locus with their normalised STR windows (reference: wrapper.py:44-54).
-    The raw int16 signal of every saved read is pulled from its annotated single-read fast5
-    (needs h5py, exactly as the reference does) and all reads are spike-filtered, MAD
-    normalised and sliced in one GPU launch."""
-    try:
-        import h5py
-    except ImportError as exc:
-        raise ImportError('reading fast5 files needs h5py (with the VBZ plugin for compressed files); '
-                          'pass an explicit workload to main_wrapper instead') from exc
+    The raw int16 signal of every saved read comes from its annotated single-read fast5
+    (``<locus>/fast5/<run_id>/annot/<read>.fast5``, what the reference's extraction step
+    writes) or, for a caller-only run prepared straight from a sequencing run's multi-read
+    files, from the file named in the row's ``fast5_path`` column (see caller_only.py).
+    All reads are spike-filtered, MAD normalised and sliced in one GPU launch."""
+    from .fast5 import raw_signal
     from .normalize import normalize_windows
     names, revs, raws, wins = [], [], [], []
+    has_src = 'fast5_path' in df_overview.columns
     for row in df_overview.itertuples():
         if row.saved:
             fpath = os.path.join(path, tmpl.FAST5_SUBDIR, str(row.run_id), tmpl.ANNOT_SUBDIR, row.Index + '.fast5')
-            with h5py.File(fpath, 'r') as fh:
-                rname = list(fh['Raw']['Reads'].keys())[0]
-                raws.append(np.asarray(fh['Raw']['Reads'][rname]['Signal']))
+            if os.path.exists(fpath):
+                raws.append(raw_signal(fpath))
+            elif has_src and isinstance(row.fast5_path, str) and os.path.exists(row.fast5_path):
+                raws.append(raw_signal(row.fast5_path, row.Index))
+            else:
+                raise FileNotFoundError(f'no fast5 for read {row.Index}: {fpath}')
             names.append(row.Index)
             revs.append(bool(row.reverse))
             wins.append((int(row.l_start_raw), int(row.r_end_raw)))
