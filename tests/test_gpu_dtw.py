@@ -178,14 +178,17 @@ def test_call_arrays_pipelined_chunks_equal_single_call(engine):
             assert np.array_equal(got['seq2'][a:a + n], s1[b:b + n])
 
 
-@pytest.mark.parametrize('name,flank_arg', [('HD', 200), ('AAAT', 160), ('DM2', 230)])
+@pytest.mark.parametrize('name,flank_arg', [('HD', 120), ('AAAT', 121), ('DM2', 123), ('CAN', 122)])
 def test_open_end_band(engine, oracle_c, name, flank_arg):
-    """flank_length larger than the real right flank puts the end band's cut inside the repeat
-    region, where back edges lead from kept states into skipped ones: the kernel must then keep
-    the per-cell band test for every banded row (DevAutomaton.band_closed == 0)."""
+    """A flank_length a little larger than the real right flank puts the end band's cut inside
+    the repeat region (seq_idx counts regex positions, the loop body once), where back edges
+    lead from kept states into skipped ones: the kernel must then keep the per-cell band test
+    for every banded row (DevAutomaton.band_closed == 0)."""
     locus = synth.make_locus(name, seed=31, flank_length=110)
     stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
     ids = [engine.add_automaton(s, flank_arg) for s in stas]
+    assert all(engine.automata[i].info()['band_closed'] == 0 for i in ids)
+    assert engine.automata[engine.add_automaton(stas[0], 110)].info()['band_closed'] == 1
     reads = synth.make_reads(locus, 5, seed=131)
     sigs = [r.signal for r in reads]
     aut = [ids[int(r.reverse)] for r in reads]

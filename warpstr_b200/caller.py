@@ -240,7 +240,13 @@ class CallerEngine:
         off = np.asarray(off, dtype=np.int64)
         aut = np.asarray(aut, dtype=np.int32)
         rev = np.asarray(rev, dtype=np.uint8)
-        bounds = list(range(0, n, max(1, chunk_reads))) + [n]
+        # chunk boundaries: a short first chunk (its copy is the only one nothing overlaps), then
+        # doubling up to chunk_reads
+        step = max(1, chunk_reads)
+        bounds, size = [0], max(1, step // 8)
+        while bounds[-1] < n:
+            bounds.append(min(n, bounds[-1] + size))
+            size = min(step, size * 2)
         cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
         seq_off = np.zeros(n + 1, dtype=np.int64)
         seq_off[1:] = np.cumsum(cap)

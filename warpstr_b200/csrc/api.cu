@@ -110,7 +110,8 @@ struct Split {
     unsigned mv_mask;   // bit mv set = instantiated for that min_values_per_state
 };
 // keep in sync with wstr_launch_fill in dtw.cu
-const Split kSplits[] = {{6, 2, 0x38}, {4, 4, 0x10}, {8, 2, 0x10}, {6, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
+const Split kSplits[] = {{7, 1, 0x10}, {6, 2, 0x38}, {8, 1, 0x10}, {4, 4, 0x10}, {8, 2, 0x10},
+                         {6, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
 
 struct Layout {
     int KC = 0, KG = 0, DEG = 2, n_lanes = 0, n_generic = 0;
@@ -434,8 +435,9 @@ extern "C" int wstr_automaton_destroy(wstr_automaton *a) {
 
 extern "C" int wstr_automaton_info(const wstr_automaton *a, int32_t *info, int32_t n_info) {
     if (!a || !info) return WSTR_ERR_INVALID_ARGUMENT;
-    const int32_t vals[7] = {a->dev.K, a->dev.NB, a->dev.KC, a->dev.KG, a->dev.S, a->n_edges, a->n_generic};
-    for (int i = 0; i < n_info && i < 7; ++i) info[i] = vals[i];
+    const int32_t vals[8] = {a->dev.K,  a->dev.NB,  a->dev.KC,     a->dev.KG,
+                             a->dev.S,  a->n_edges, a->n_generic,  a->dev.band_closed};
+    for (int i = 0; i < n_info && i < 8; ++i) info[i] = vals[i];
     return WSTR_OK;
 }
 

@@ -486,7 +486,7 @@ struct alignas(16) FillSmem {
 #define WSTR_FILL_BOUNDS __maxnreg__(WSTR_MAXNREG)
 #else
 #define WSTR_FILL_BOUNDS \
-    __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 8 ? WSTR_K8_BLOCKS : (KC + KG <= 12 ? 3 : 2)))
+    __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 9 ? WSTR_K8_BLOCKS : (KC + KG <= 12 ? 3 : 2)))
 #endif
 template <int KC, int KG, int DEG, int MV>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
@@ -675,7 +675,9 @@ int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaS
     if (deg > 4) return WSTR_ERR_UNSUPPORTED;
 #define WSTR_CASE(KC_, KG_, MV_) \
     if (kc == KC_ && kg == KG_ && mv == MV_) return launch_fill_deg<KC_, KG_, MV_>(deg, p, s);
+    WSTR_CASE(7, 1, 4)
     WSTR_CASE(6, 2, 4)
+    WSTR_CASE(8, 1, 4)
     WSTR_CASE(6, 2, 3)
     WSTR_CASE(6, 2, 5)
     WSTR_CASE(4, 4, 4)
