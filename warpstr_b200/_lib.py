@@ -277,7 +277,7 @@ def call_batch(automata: Sequence[DeviceAutomaton], read_automaton, read_reverse
     check(rc, 'wstr_call_batch')
 
 
-PROFILE_CATEGORIES = ('dp_fill_traceback', 'midstage', 'normalize', 'pore_lookup')
+PROFILE_CATEGORIES = ('dp_fill_traceback', 'midstage', 'normalize', 'pore_lookup', 'plan_upload')
 
 
 def profile_enable(on: bool = True) -> None:
@@ -285,7 +285,8 @@ def profile_enable(on: bool = True) -> None:
 
 
 def profile_read() -> dict:
-    ms = np.zeros(4, dtype=np.float64)
-    cnt = np.zeros(4, dtype=np.int32)
-    check(lib().wstr_profile_read(_ptr(ms, c_f64p), _ptr(cnt, c_i32p), 4), 'wstr_profile_read')
+    n = len(PROFILE_CATEGORIES)
+    ms = np.zeros(n, dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int32)
+    check(lib().wstr_profile_read(_ptr(ms, c_f64p), _ptr(cnt, c_i32p), n), 'wstr_profile_read')
     return {name: {'ms': float(ms[i]), 'launches': int(cnt[i])} for i, name in enumerate(PROFILE_CATEGORIES)}

@@ -97,9 +97,11 @@ class CallerEngine:
         self.automata: List[_lib.DeviceAutomaton] = []
         self.tables: List[dict] = []
         self._ws = None
+        self._ws_at_limit = False
         self._copy_stream = None
         self.timeline = None      # set to a list to collect (label, CUDA event) pairs from call_arrays
         self._host_out = None
+        self._dev_cache = {}
 
     # -- automata ------------------------------------------------------------------------
     def add_automaton(self, sta, flank_length: int) -> int:
@@ -117,13 +119,20 @@ class CallerEngine:
 
     # -- device helpers ---------------------------------------------------------------------
     def _workspace(self, need: int):
+        """Device workspace of ``need`` bytes, or as much as the memory limit allows (the library
+        then works in waves).  The buffer only grows; cudaMemGetInfo is asked only when it has
+        to (the call can block for tens of milliseconds while the GPU is busy)."""
         import torch
+        ws = self._ws
+        if ws is not None and (ws.numel() >= need or self._ws_at_limit):
+            return ws
         limit = self.workspace_limit
         if limit is None:
             free, _ = torch.cuda.mem_get_info(self.device)
-            limit = int(free * 0.6) + (self._ws.numel() if self._ws is not None else 0)
+            limit = int(free * 0.6) + (ws.numel() if ws is not None else 0)
         size = min(need, max(limit, 1 << 20))
-        if self._ws is None or self._ws.numel() < size:
+        self._ws_at_limit = size < need
+        if ws is None or ws.numel() < size:
             self._ws = None
             self._ws = torch.empty(size, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -193,7 +202,8 @@ class CallerEngine:
         d_sig = host.to(self.device, non_blocking=True)
         return d_sig, off, lengths, np.asarray(aut_ids, dtype=np.int32), np.asarray(reverse, dtype=np.uint8)
 
-    def call_packed(self, d_sig, off, lengths, aut, rev, want_seq: bool = True, want_debug: bool = False):
+    def call_packed(self, d_sig, off, lengths, aut, rev, want_seq: bool = True, want_debug: bool = False,
+                    into: Optional[dict] = None):
         """wstr_call_batch on device-resident signals.  Returns a dict of device tensors
         (len1, len2, cost1, cost2, status[, seq1, seq2, seq_off])."""
         import torch
@@ -201,20 +211,25 @@ class CallerEngine:
         with torch.cuda.device(self.device):
             need = _lib.call_workspace_bytes(self.automata, aut, lengths)
             ws = self._workspace(need)
-            o = dict(
-                len1=torch.empty(n, dtype=torch.int32, device=self.device),
-                len2=torch.empty(n, dtype=torch.int32, device=self.device),
-                cost1=torch.empty(n, dtype=torch.float64, device=self.device),
-                cost2=torch.empty(n, dtype=torch.float64, device=self.device),
-                status=torch.zeros(n, dtype=torch.int32, device=self.device))
+            if into is not None:      # caller-owned result buffers (views of the right sizes)
+                o = dict(into)
+                o['status'].zero_()
+            else:
+                o = dict(
+                    len1=torch.empty(n, dtype=torch.int32, device=self.device),
+                    len2=torch.empty(n, dtype=torch.int32, device=self.device),
+                    cost1=torch.empty(n, dtype=torch.float64, device=self.device),
+                    cost2=torch.empty(n, dtype=torch.float64, device=self.device),
+                    status=torch.zeros(n, dtype=torch.int32, device=self.device))
             seq_off = None
             if want_seq:
                 cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
                 seq_off = np.zeros(n, dtype=np.int64)
                 seq_off[1:] = np.cumsum(cap[:-1])
                 total = int(cap.sum())
-                o['seq1'] = torch.empty(total, dtype=torch.uint8, device=self.device)
-                o['seq2'] = torch.empty(total, dtype=torch.uint8, device=self.device)
+                if into is None:
+                    o['seq1'] = torch.empty(total, dtype=torch.uint8, device=self.device)
+                    o['seq2'] = torch.empty(total, dtype=torch.uint8, device=self.device)
                 o['seq_off'] = seq_off
             if want_debug:   # intermediate products, for the parity tests
                 o['trace1'] = torch.empty(d_sig.numel(), dtype=torch.int32, device=self.device)
@@ -228,7 +243,7 @@ class CallerEngine:
         return o
 
     def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True,
-                    chunk_reads: int = 25000) -> Dict[str, np.ndarray]:
+                    chunk_reads: int = 50000) -> Dict[str, np.ndarray]:
         """Array-level end-to-end call: (pinned) host signal buffer in, host arrays out --
         len1 ('orig'), len2 ('results'), cost1, cost2, status and, optionally, the decoded
         sequence bytes.  The batch is cut into chunks of ``chunk_reads`` reads; one copy stream
@@ -243,7 +258,7 @@ class CallerEngine:
         # chunk boundaries: a short first chunk (its copy is the only one nothing overlaps), then
         # doubling up to chunk_reads
         step = max(1, chunk_reads)
-        bounds, size = [0], max(1, step // 8)
+        bounds, size = [0], max(1, step // 16)
         while bounds[-1] < n:
             bounds.append(min(n, bounds[-1] + size))
             size = min(step, size * 2)
@@ -257,7 +272,15 @@ class CallerEngine:
                 self._copy_stream = (torch.cuda.Stream(), torch.cuda.Stream())
             cs_in, cs_out = self._copy_stream
             total = int(off[-1] + ((int(lengths[-1]) + 1) & ~1) + 2) if n else 0
-            d_sig = torch.empty(min(total, host_signal.numel()), dtype=torch.float64, device=self.device)
+            # device-side signal and result buffers live on the engine and only ever grow, so the
+            # chunk loop makes no allocator calls
+            d_sig = self._device_buffer('sig', min(total, host_signal.numel()), torch.float64)
+            dev = {k: self._device_buffer(k, n, dt) for k, dt in
+                   (('len1', torch.int32), ('len2', torch.int32), ('cost1', torch.float64),
+                    ('cost2', torch.float64), ('status', torch.int32))}
+            if want_seq:
+                dev['seq1'] = self._device_buffer('seq1', int(seq_off[-1]), torch.uint8)
+                dev['seq2'] = self._device_buffer('seq2', int(seq_off[-1]), torch.uint8)
             cs_in.wait_stream(comp)
             cs_out.wait_stream(comp)
             chunks = list(zip(bounds[:-1], bounds[1:]))
@@ -282,17 +305,21 @@ class CallerEngine:
                 return lo, hi, ev
 
             keep = []
-            nxt = send(*chunks[0]) if chunks else None
+            # every chunk's copy is queued up front (the calls stage their metadata through a
+            # kernel, so nothing of theirs waits behind these copies on the DMA engine); the
+            # host only has to keep the compute stream fed
+            sent = [send(a, b) for a, b in chunks]
             for ci, (a, b) in enumerate(chunks):
-                lo, hi, ev = nxt
+                lo, hi, ev = sent[ci]
                 comp.wait_event(ev)
                 mark(f'call{a} begin', comp)
-                o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b], want_seq=want_seq)
+                into = {k: dev[k][a:b] for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+                if want_seq:
+                    into['seq1'] = dev['seq1'][int(seq_off[a]):int(seq_off[b])]
+                    into['seq2'] = dev['seq2'][int(seq_off[a]):int(seq_off[b])]
+                o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b], want_seq=want_seq,
+                                     into=into)
                 mark(f'call{a} end', comp)
-                # the call stages its own metadata through a kernel, so the DMA engine is free for the
-                # next chunk's signal while this one computes
-                if ci + 1 < len(chunks):
-                    nxt = send(*chunks[ci + 1])
                 done = torch.cuda.Event()
                 done.record(comp)
                 with torch.cuda.stream(cs_out):                 # results back while the next chunk computes
@@ -314,6 +341,15 @@ class CallerEngine:
             res['seq2'] = out['seq2'][:int(seq_off[-1])].numpy()
             res['seq_off'] = seq_off[:-1]
         return res
+
+    def _device_buffer(self, name: str, numel: int, dtype):
+        import torch
+        cur = self._dev_cache.get(name)
+        if cur is None or cur.numel() < numel or cur.dtype != dtype:
+            self._dev_cache[name] = None
+            cur = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self._dev_cache[name] = cur
+        return cur[:numel]
 
     def _host_results(self, n: int, seq_bytes: int):
         """Pinned host buffers for the per-read results, grown on demand and reused."""

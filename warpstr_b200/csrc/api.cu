@@ -490,6 +490,17 @@ int stage_acquire(size_t bytes, StageSlot **out) {
     return WSTR_OK;
 }
 
+// work counters are cleared by a kernel, not cudaMemsetAsync: the driver may run a memset on a
+// copy engine, behind whatever bulk copies a pipelining caller has queued there
+__global__ void zero_kernel(int32_t *p, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
+}
+int zero_counters(int32_t *d, int n, cudaStream_t s) {
+    zero_kernel<<<1, 64, 0, s>>>(d, n);
+    WSTR_CUDA(cudaGetLastError());
+    return WSTR_OK;
+}
+
 __global__ void upload_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = src[i];
@@ -501,7 +512,9 @@ int stage_upload(StageSlot *sl, void *d_dst, size_t bytes, cudaStream_t s) {
     const int grid = (int)std::min<size_t>((n16 + 255) / 256, 512);
     void *d_src = nullptr;
     WSTR_CUDA(cudaHostGetDevicePointer(&d_src, sl->h, 0));
+    wstr_prof_begin(4, s);
     upload_kernel<<<grid, 256, 0, s>>>(static_cast<uint4 *>(d_dst), static_cast<const uint4 *>(d_src), n16);
+    wstr_prof_end(s);
     WSTR_CUDA(cudaGetLastError());
     WSTR_CUDA(cudaEventRecord(sl->done, s));
     sl->pending = true;
@@ -624,7 +637,7 @@ int run_fill(const std::vector<Wave> &waves, const FillDevice &fd, int mv, const
              const uint32_t *d_maskbits, int32_t *d_trace, double *d_end_cost, int32_t *d_status, int respect_status,
              cudaStream_t s) {
     for (const Wave &w : waves) {
-        WSTR_CUDA(cudaMemsetAsync(fd.counters, 0, kCounters * sizeof(int32_t), s));
+        if (int zrc = zero_counters(fd.counters, kCounters, s)) return zrc;
         for (const FillLaunch &fl : w.launches) {
             FillParams fp;
             fp.auts = fd.auts;
@@ -892,7 +905,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     mp.sis = params->states_in_segment;
     mp.threshold = params->threshold;
     mp.max_std = params->max_std;
-    WSTR_CUDA(cudaMemsetAsync(d_queue, 0, 256, s));
+    if (int zrc = zero_counters(d_queue, 64, s)) return zrc;
     wstr_prof_begin(1, s);
     rc = wstr_launch_midstage(mp, false, s);
     wstr_prof_end(s);
@@ -908,7 +921,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     mp.len = out->d_len2;
     mp.cost = out->d_cost2;
     mp.seq = out->d_seq2;
-    WSTR_CUDA(cudaMemsetAsync(d_queue, 0, 256, s));
+    if (int zrc = zero_counters(d_queue, 64, s)) return zrc;
     wstr_prof_begin(1, s);
     rc = wstr_launch_midstage(mp, true, s);
     wstr_prof_end(s);
