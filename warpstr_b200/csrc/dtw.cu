@@ -371,13 +371,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 template <int KC, int KG, int DEG>
 __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int T, const uint32_t *dir,
                                                const uint32_t *mw, int32_t *tr, int32_t *status_slot,
-                                               const int lane, uint32_t *win, uint64_t *bar, uint32_t &phase_bits) {
+                                               const int lane, uint32_t *win, uint64_t *bar, uint32_t &phase_bits,
+                                               const int32_t *spred) {
     constexpr int K = KC + KG;
     constexpr int NB = DirFmt<KC, KG, DEG>::NB, RPW = DirFmt<KC, KG, DEG>::RPW;
     using G = TbGeom<RPW>;
     constexpr int WRW = G::WRW, ROWS = G::ROWS, NBUF = G::NBUF;
     const int mv = A->mv;
-    const int32_t *pred = A->pred_tab;
     const int wtop = (T - 1) / RPW;                  // last word row
     const int wmin = mv / RPW;                       // first word row that was written
     const int nwin = wtop / WRW + 1;
@@ -413,42 +413,45 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
         const int lo = hi - ROWS + 1 > 0 ? hi - ROWS + 1 : 0;
         if (i >= lo && i > 0 && !failed) {
             const int row = hi - lane;
-            const bool mine = lane < ROWS && row >= lo;
+            // rows of this window the walk enters from above (rows above i were emitted with the
+            // previous window's last move)
+            const bool mine = lane < ROWS && row >= lo && row <= i;
+            const bool coded = mine && row >= mv;
             uint32_t mb = 0u;
-            if (mw && mine && row < T) mb = (__ldg(mw + (row >> 5)) >> (row & 31)) & 1u;
+            if (mw && mine) mb = (__ldg(mw + (row >> 5)) >> (row & 31)) & 1u;
             const int wr = mine ? row / RPW : wh;
             const uint32_t *wslot = win + (b * WRW + (wr - (wh - WRW + 1))) * 32;
             const int fsh = (row - wr * RPW) * NB;      // this row's bit field inside its word
-            int my = -1;
+            int my = st;                                // state emitted for this lane's row
             for (;;) {
                 const int hl = pos / K;
                 const int u = pos - hl * K;
+                // code of the path's state in this lane's row (0 = stay)
                 uint32_t nib = 0u;
-                if (mine && row <= i && row >= mv) {
+                if (coded && row <= i) {
                     const uint32_t f = wslot[hl] >> fsh;
                     nib = u < KC ? (f >> u) & 1u : (f >> (KC + (u - KC) * DEG)) & ((1u << DEG) - 1u);
                 }
                 const uint32_t moves = __ballot_sync(FULL, nib != 0u);
                 if (moves == 0u) {                          // stays down to the window's last row
-                    if (mine && row <= i) my = st;
                     i = lo - 1;
                     break;
                 }
                 const int tm = __ffs(moves) - 1;            // lane of the first row that leaves the state
                 const int rm = hi - tm;
-                if (mine && row <= i && row >= rm) my = st; // the stays above it and the row itself
                 const uint32_t nibm = __shfl_sync(FULL, nib, tm);
-                const int code = 32 - __clz(nibm);          // last candidate that took the lead
                 const int back = mv - static_cast<int>(__shfl_sync(FULL, mb, tm));
-                const int32_t pp = __ldg(pred + pos * WSTR_PRED_STRIDE + code);
+                const int code = 31 - __clz(nibm);          // last candidate that took the lead
+                const int32_t pp = spred[pos * DEG + code];
                 if (rm < back || pp < 0) {
                     failed = true;
                     break;
                 }
                 const int pst = pp >> 16;
-                // the skipped rows rm-1 .. rm-back+1 belong to the predecessor
-                if (mine && row < rm && row > rm - back) my = pst;
-                if (rm - back + 1 < lo) {                   // ... some of them lie below this window
+                // the move row keeps the state it leaves; every row below it belongs to the
+                // predecessor until a later move says otherwise
+                if (row < rm) my = pst;
+                if (rm - back + 1 < lo) {                   // skipped rows below this window
                     const int r = lo - 1 - lane;
                     if (lane < back - 1 && r > rm - back) tr[r] = pst;
                 }
@@ -457,7 +460,7 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
                 st = pst;
                 if (i < lo || i <= 0) break;
             }
-            if (mine && my >= 0) tr[row] = my;
+            if (mine) tr[row] = my;
         }
         __syncwarp();                                       // every lane is done with this buffer
         if (c + NBUF < nwin) issue(c + NBUF);
@@ -475,6 +478,7 @@ struct alignas(16) FillSmem {
     double sig[2][CH];                   // look-ahead reads may run up to 2*(mv-1) samples past a tile (into Q: unused)
     double Q[MV - 1][q_row_len<KG>()];   // one published buffer per pipeline phase
     uint32_t win[G::WORDS];              // traceback windows
+    int32_t pred[(KC + KG) * 32 * DEG];  // traceback: (state << 16 | position) of the predecessor, by position and code
     uint64_t bar[2];                     // signal tiles
     uint64_t tbar[G::NBUF];              // traceback windows
 };
@@ -536,6 +540,8 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
 #pragma unroll
             for (int g = 0; g < KG; ++g) lc.gsrc[g] = __ldg(A->lane_tab + lane * WSTR_LANE_TAB_STRIDE + 2 + g);
             v0 = __ldg(A->v_pos + A->init_pos[0]);
+            for (int e = lane; e < K * 32 * DEG; e += 32)
+                sm.pred[e] = __ldg(A->pred_tab + (e / DEG) * WSTR_PRED_STRIDE + 1 + (e % DEG));
             cached_aut = m.aut;
         }
 
@@ -634,7 +640,7 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
         __syncwarp();   // this warp's direction words are visible to all of its lanes
 #ifndef WSTR_NO_TRACEBACK   // (experiment switch: time the fill alone)
         traceback_warp<KC, KG, DEG>(A, T, dir, mw_ptr, p.trace + m.sig_off, p.status + m.read, lane, sm.win, sm.tbar,
-                                    tb_phase);
+                                    tb_phase, sm.pred);
 #endif
     }
 }
