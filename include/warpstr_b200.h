@@ -102,7 +102,11 @@ int wstr_automaton_layout(const wstr_automaton *a, int32_t *state_of_pos, int32_
 
 /* Bytes of device workspace wstr_warp_batch / wstr_call_batch need to process all reads in
  * one wave.  A smaller workspace is legal (>= the value returned for the single largest read
- * plus metadata): the batch is then processed in several waves. */
+ * plus metadata): the batch is then processed in several waves.
+ * Both calls are asynchronous with respect to the host: the per-call plan (read records,
+ * processing order) is written into pinned mapped memory and copied in by a kernel on `stream`;
+ * no cudaMemcpy/cudaMemset is issued, so the copy engines stay free for the caller's own
+ * transfers.  One CUDA device per process. */
 int64_t wstr_warp_workspace_bytes(wstr_automaton *const *automata, int32_t n_automata,
                                   const int32_t *read_automaton, const int32_t *lengths,
                                   int32_t n_reads);
@@ -170,8 +174,8 @@ int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,
 /* ---- kernel timing ------------------------------------------------------------------------------
  * When enabled, every kernel launch of this library is bracketed by CUDA events on the launching
  * stream.  wstr_profile_read waits for them and returns, per category (0 DP fill + traceback,
- * 1 mid-stage, 2 normalisation, 3 pore lookup), the summed device time in ms and the number of
- * launches since the last read. */
+ * 1 mid-stage, 2 normalisation, 3 pore lookup, 4 upload of the per-call host plan), the summed
+ * device time in ms and the number of launches since the last read. */
 int wstr_profile_enable(int32_t on);
 int wstr_profile_read(double *ms, int32_t *launches, int32_t n_categories);
 
