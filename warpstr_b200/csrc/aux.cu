@@ -16,30 +16,57 @@
 // ------------------------------------------------------------------------------------------
 // (1) pore-model lookup
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t base_code(uint8_t c, bool &ok) {
+    switch (c) {
+        case 'A': return 0u;
+        case 'C': return 1u;
+        case 'G': return 2u;
+        case 'T': return 3u;
+        default: ok = false; return 0u;
+    }
+}
+
+// Every thread produces VPT consecutive levels from one rolling 2-bit-packed k-mer index
+// (VPT + k - 1 byte loads instead of VPT * k) and writes them with 16-byte stores when the
+// output is aligned for it.
+constexpr int PORE_VPT = 4;
 __global__ void pore_lookup_kernel(const uint8_t *__restrict__ seq, int64_t n_out, const double *__restrict__ table,
-                                   int k, double *__restrict__ out, int32_t *bad) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_out;
-         i += (int64_t)gridDim.x * blockDim.x) {
+                                   int k, double *__restrict__ out, int32_t *bad, int vec_ok) {
+    const uint32_t mask = k >= 16 ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * PORE_VPT; i < n_out;
+         i += (int64_t)gridDim.x * blockDim.x * PORE_VPT) {
         uint32_t idx = 0;
-        bool ok = true;
-        for (int p = 0; p < k; ++p) {
-            const uint8_t c = seq[i + p];
-            uint32_t code;
-            switch (c) {
-                case 'A': code = 0; break;
-                case 'C': code = 1; break;
-                case 'G': code = 2; break;
-                case 'T': code = 3; break;
-                default: code = 0; ok = false;
+        int valid = 0;                       // consecutive valid bases ending at the current one
+        for (int p = 0; p < k - 1; ++p) {
+            bool ok = true;
+            const uint32_t c = base_code(seq[i + p], ok);
+            idx = (idx << 2) | c;
+            valid = ok ? valid + 1 : 0;
+        }
+        double v[PORE_VPT];
+        int n_bad = 0;
+#pragma unroll
+        for (int j = 0; j < PORE_VPT; ++j) {
+            v[j] = nan;
+            if (i + j < n_out) {
+                bool ok = true;
+                const uint32_t c = base_code(seq[i + j + k - 1], ok);
+                idx = ((idx << 2) | c) & mask;
+                valid = ok ? valid + 1 : 0;
+                if (valid >= k) v[j] = __ldg(table + idx);
+                else ++n_bad;
             }
-            idx = idx * 4u + code;
         }
-        if (ok) {
-            out[i] = __ldg(table + idx);
+        if (vec_ok && i + PORE_VPT <= n_out) {
+            reinterpret_cast<double2 *>(out + i)[0] = make_double2(v[0], v[1]);
+            reinterpret_cast<double2 *>(out + i)[1] = make_double2(v[2], v[3]);
         } else {
-            out[i] = __longlong_as_double(0x7ff8000000000000LL);
-            if (bad) atomicAdd(bad, 1);
+#pragma unroll
+            for (int j = 0; j < PORE_VPT; ++j)
+                if (i + j < n_out) out[i + j] = v[j];
         }
+        if (n_bad && bad) atomicAdd(bad, n_bad);
     }
 }
 
@@ -49,11 +76,12 @@ extern "C" int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d
     const int64_t n_out = n - k + 1;
     if (n_out <= 0) return WSTR_OK;
     const int threads = 256;
-    int64_t blocks = (n_out + threads - 1) / threads;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int64_t blocks = (n_out + (int64_t)threads * PORE_VPT - 1) / ((int64_t)threads * PORE_VPT);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
     wstr_prof_begin(3, static_cast<cudaStream_t>(stream));
     pore_lookup_kernel<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(d_seq, n_out, d_table, k, d_out,
-                                                                                       d_bad);
+                                                                                       d_bad, vec_ok);
     wstr_prof_end(static_cast<cudaStream_t>(stream));
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;
@@ -85,17 +113,18 @@ struct NormParams {
 
 struct NormSmem {
     uint32_t hist[HBINS];
-    int16_t tile[TILE + 8];
-    int16_t filt[TILE];
+    // tile[HALO + t] = sample t of the current tile; tile[HALO-2], tile[HALO-1] = the two
+    // (patched) samples before it.  HALO = 8 keeps the tile 16-byte aligned for vector access.
+    alignas(16) int16_t tile[TILE + 16];
     uint16_t spikes[TILE];
     int32_t warp_sums[NT / 32];
     int32_t n_spikes;
     int32_t next_read;
     int32_t vmin, vmax;
     int32_t ghist_dirty;
-    int32_t ranks_val[6];
     double shift, scale;
 };
+constexpr int HALO = 8;
 
 __device__ __forceinline__ uint32_t hcount(const NormSmem &sm, const uint32_t *gh, int v) {
     if (v >= 0 && v < HBINS) return sm.hist[v];
@@ -171,6 +200,11 @@ __device__ double absdev_at_rank(const NormSmem &sm, const uint32_t *gh, double 
     return 0.0;
 }
 
+// One CTA per read, one pass over the samples in tiles of 2048.  The read is walked from the
+// 16-byte boundary at or before its first sample, so every thread loads its 8 samples with one
+// aligned 16-byte load, a tile ahead of their use (samples in front of / behind the read are
+// masked).  Per tile there is a single barrier unless the tile holds an out-of-range sample
+// (Brute) or a median filter is on.
 __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NormSmem &sm = *reinterpret_cast<NormSmem *>(smem_raw);
@@ -195,34 +229,64 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
             sm.vmax = -32768;
             sm.ghist_dirty = 0;
         }
-        if (tid < 8) sm.tile[tid] = 0;
+        if (tid < HALO) sm.tile[tid] = 0;
         __syncthreads();
 
+        // sample index g (0-based in the read) of tile k, thread tid, element u: k*TILE + tid*PER + u - mis
+        const int mis = (int)((reinterpret_cast<uintptr_t>(raw) >> 1) & 7);
+        const uint4 *vec = reinterpret_cast<const uint4 *>(raw - mis);
+        const int64_t n_tiles = (N + mis + TILE - 1) / TILE;
+        const int64_t n_vec = (N + mis + PER - 1) / PER;
+        auto fetch = [&](int64_t k) {
+            const int64_t v = k * NT + tid;
+            return v < n_vec ? __ldg(vec + v) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        uint4 nxt = fetch(0);
         int lmin = 32767, lmax = -32768;
-        for (int64_t t0 = 0; t0 < N; t0 += TILE) {
-            const int len = (int)min((int64_t)TILE, N - t0);
-            // tile[2 + t] = sample t0 + t; two halo samples on each side
-            for (int t = tid; t < len + 2; t += NT) {
-                const int64_t g = t0 + t;
-                sm.tile[2 + t] = g < N ? raw[g] : (int16_t)0;
+        for (int64_t k = 0; k < n_tiles; ++k) {
+            union {
+                uint4 q;
+                int16_t h[PER];
+            } cur;
+            cur.q = nxt;
+            if (k + 1 < n_tiles) nxt = fetch(k + 1);
+            const int64_t t_base = k * TILE - mis;                       // read index of tile element 0
+            const int64_t g0 = t_base + tid * PER;                       // ... of this thread's first sample
+            // block-uniform: every sample of the tile belongs to the read / the tile meets the window
+            const bool interior = t_base >= 0 && t_base + TILE <= N;
+            const bool in_window = t_base <= hi && t_base + TILE > lo;
+            int tmin, tmax;                                              // over this thread's valid samples
+            if (interior) {                                              // two samples per instruction
+                const unsigned mn = __vmins2(__vmins2(cur.q.x, cur.q.y), __vmins2(cur.q.z, cur.q.w));
+                const unsigned mx = __vmaxs2(__vmaxs2(cur.q.x, cur.q.y), __vmaxs2(cur.q.z, cur.q.w));
+                tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
+                tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
+            } else {
+                tmin = 32767;
+                tmax = -32768;
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int64_t g = g0 + u;
+                    if (g >= 0 && g < N) {
+                        tmin = min(tmin, (int)cur.h[u]);
+                        tmax = max(tmax, (int)cur.h[u]);
+                    } else {
+                        cur.h[u] = 0;                                    // zero padding (scipy medfilt's, too)
+                    }
+                }
             }
-            if (p.spike_mode != 1 && tid < 2) {   // median filters look at raw neighbours
-                const int64_t g = t0 - 2 + tid;
-                sm.tile[tid] = g >= 0 ? raw[g] : (int16_t)0;
-            }
-            if (tid == 0) sm.n_spikes = 0;
-            __syncthreads();
+            const bool spike = tmin < 250 || tmax > 1000;               // Brute's test on the original samples
+            *reinterpret_cast<uint4 *>(&sm.tile[HALO + tid * PER]) = cur.q;
+            const bool slow = p.spike_mode == 1 ? __syncthreads_or(spike) != 0 : (__syncthreads(), p.spike_mode != 0);
 
-            if (p.spike_mode == 1) {
+            if (slow && p.spike_mode == 1) {
                 // Brute (fast5.py:90-101): ordered list of out-of-range samples of this tile ...
                 int cnt = 0;
-                const int base = tid * PER;
                 bool flag[PER];
 #pragma unroll
                 for (int u = 0; u < PER; ++u) {
-                    const int t = base + u;
-                    const int16_t vv = t < len ? sm.tile[2 + t] : (int16_t)500;
-                    flag[u] = (vv > 1000) || (vv < 250);
+                    const int64_t g = g0 + u;
+                    flag[u] = g >= 0 && g < N && (cur.h[u] > 1000 || cur.h[u] < 250);
                     cnt += flag[u];
                 }
                 int inc = cnt;
@@ -238,56 +302,96 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
                 int pos = woff + inc - cnt;
 #pragma unroll
                 for (int u = 0; u < PER; ++u)
-                    if (flag[u]) sm.spikes[pos++] = (uint16_t)(base + u);
+                    if (flag[u]) sm.spikes[pos++] = (uint16_t)(tid * PER + u);
                 if (tid == NT - 1) sm.n_spikes = woff + inc;
                 __syncthreads();
                 // ... patched one after the other: later medians see earlier fixes
                 if (tid == 0) {
                     for (int s = 0; s < sm.n_spikes; ++s) {
                         const int t = sm.spikes[s];
-                        const int64_t g = t0 + t;
+                        const int64_t g = t_base + t;
                         if (g > 2) {
                             int16_t w5[5];
                             const int n = (int)min((int64_t)5, N - (g - 2));
-                            for (int u = 0; u < n; ++u) w5[u] = sm.tile[t + u];   // samples g-2 .. g-2+n-1
-                            sm.tile[2 + t] = median_small(w5, n);
+                            for (int u = 0; u < n; ++u) {                // samples g-2 .. g-2+n-1
+                                const int e = t - 2 + u;                 // tile element (-2, -1 = carried)
+                                w5[u] = e < TILE ? sm.tile[HALO + e] : raw[g - 2 + u];   // not yet patched: raw
+                            }
+                            sm.tile[HALO + t] = median_small(w5, n);
                         }
                     }
                 }
                 __syncthreads();
-            } else if (p.spike_mode == 3 || p.spike_mode == 5) {
-                // scipy.signal.medfilt: zero-padded running median (fast5.py:72-75)
+                cur.q = *reinterpret_cast<const uint4 *>(&sm.tile[HALO + tid * PER]);
+                // (a patched value is a median of original values: tmin/tmax still bound it)
+            } else if (slow) {
+                // scipy.signal.medfilt: zero-padded running median of the raw samples (fast5.py:72-75)
                 const int h = p.spike_mode / 2;
-                for (int t = tid; t < len; t += NT) {
+                int16_t res[PER];
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
                     int16_t w5[5];
-                    for (int u = -h; u <= h; ++u) {
-                        const int64_t g = t0 + t + u;
-                        w5[u + h] = (g >= 0 && g < N) ? sm.tile[2 + t + u] : (int16_t)0;
+                    for (int d = -h; d <= h; ++d) {
+                        const int e = tid * PER + u + d;
+                        const int64_t g = t_base + e;
+                        int16_t vv = 0;
+                        if (g >= 0 && g < N) vv = e < TILE ? sm.tile[HALO + e] : raw[g];
+                        w5[d + h] = vv;
                     }
-                    sm.filt[t] = median_small(w5, 2 * h + 1);
+                    res[u] = median_small(w5, 2 * h + 1);
                 }
-                __syncthreads();
-                for (int t = tid; t < len; t += NT) sm.tile[2 + t] = sm.filt[t];
-                __syncthreads();
+                __syncthreads();                                        // everyone has read its neighbours
+                if (tid == NT - 1) {                                    // raw carry for the next tile
+                    sm.tile[HALO - 2] = cur.h[PER - 2];
+                    sm.tile[HALO - 1] = cur.h[PER - 1];
+                }
+                tmin = 32767;                                           // the zero padding can put values
+                tmax = -32768;                                          // below the raw minimum
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    cur.h[u] = res[u];
+                    const int64_t g = g0 + u;
+                    if (g >= 0 && g < N) {
+                        tmin = min(tmin, (int)res[u]);
+                        tmax = max(tmax, (int)res[u]);
+                    }
+                }
             }
+            lmin = min(lmin, tmin);
+            lmax = max(lmax, tmax);
 
-            // histogram, extrema and the window stash
-            for (int t = tid; t < len; t += NT) {
-                const int vv = sm.tile[2 + t];
-                lmin = min(lmin, vv);
-                lmax = max(lmax, vv);
-                if (vv >= 0 && vv < HBINS) {
-                    atomicAdd(&sm.hist[vv], 1u);
-                } else {
-                    atomicAdd(&gh[vv + 32768], 1u);
-                    sm.ghist_dirty = 1;
+            // histogram
+            if (interior && tmin >= 0 && tmax < HBINS) {
+#pragma unroll
+                for (int u = 0; u < PER; ++u) atomicAdd(&sm.hist[cur.h[u]], 1u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int64_t g = g0 + u;
+                    if (g < 0 || g >= N) continue;
+                    const int vv = cur.h[u];
+                    if (vv >= 0 && vv < HBINS) {
+                        atomicAdd(&sm.hist[vv], 1u);
+                    } else {
+                        atomicAdd(&gh[vv + 32768], 1u);
+                        sm.ghist_dirty = 1;
+                    }
                 }
-                const int64_t g = t0 + t;
-                if (g >= lo && g <= hi) stash[g - lo] = (int16_t)vv;
             }
-            __syncthreads();
-            if (p.spike_mode == 1 && tid < 2) sm.tile[tid] = sm.tile[len + tid];   // patched carry
-            __syncthreads();
+            // the window's samples are parked in the tail of their own output slot
+            if (in_window) {
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int64_t g = g0 + u;
+                    if (g >= lo && g <= hi && g < N) stash[g - lo] = cur.h[u];
+                }
+            }
+            if (p.spike_mode == 1 && tid == NT - 1) {                   // patched carry for the next tile
+                sm.tile[HALO - 2] = cur.h[PER - 2];
+                sm.tile[HALO - 1] = cur.h[PER - 1];
+            }
+            // the next iteration's tile store cannot pass this tile's readers: in the slow paths they
+            // are fenced by the barriers above, in the fast path nobody reads the tile
         }
         atomicMin(&sm.vmin, lmin);
         atomicMax(&sm.vmax, lmax);
@@ -336,9 +440,9 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
         // convert the stashed int16 window in place, front to back, one tile at a time
         for (int64_t t0 = 0; t0 < Tw; t0 += TILE) {
             const int len = (int)min((int64_t)TILE, Tw - t0);
-            for (int t = tid; t < len; t += NT) sm.filt[t] = stash[t0 + t];
+            for (int t = tid; t < len; t += NT) sm.tile[HALO + t] = stash[t0 + t];
             __syncthreads();
-            for (int t = tid; t < len; t += NT) out[t0 + t] = ((double)sm.filt[t] - shift) / scale;
+            for (int t = tid; t < len; t += NT) out[t0 + t] = ((double)sm.tile[HALO + t] - shift) / scale;
             __syncthreads();
         }
         // leave the global fallback histogram clean for the next read
@@ -350,7 +454,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
 }
 
 int norm_grid(int n_reads) {
-    int g = 148 * 2;
+    int g = 148 * 5;   // 5 CTAs per SM fit (41 KB of shared memory each)
     return n_reads < g ? (n_reads < 1 ? 1 : n_reads) : g;
 }
 
