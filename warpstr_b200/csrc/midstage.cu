@@ -260,6 +260,7 @@ __device__ __forceinline__ uint8_t complement(uint8_t b) {
 struct Scratch {
     int32_t *run_start, *run_state;
     double *sv, *px, *py, *sx, *sy;
+    int32_t *sidx;       // sort scratch for long reads
 };
 
 __device__ __forceinline__ Scratch carve(unsigned char *ws, int R) {
@@ -271,8 +272,42 @@ __device__ __forceinline__ Scratch carve(unsigned char *ws, int R) {
     s.py = s.px + R;
     s.sx = s.py + R;
     s.sy = s.sx + R;
+    s.sidx = reinterpret_cast<int32_t *>(s.sy + R);
     return s;
 }
+
+// Stable ascending sort of (key[i], idx[i]), i < m, by one warp: a bitonic network in the form
+// whose compare-exchanges all point the same way (first step of every merge mirrors the block,
+// the others are butterflies), so the positions m..P-1 can be left out as virtual +inf.  Ties
+// are broken by idx, which makes the order the stable one np.argsort(kind='stable') /
+// sorted() produce.  key/idx may live in shared or global memory.
+__device__ void warp_sort_pairs(double *key, int32_t *idx, int m, int lane) {
+    int P = 1;
+    while (P < m) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int flip = j == (k >> 1) ? k - 1 : j;      // partner = i ^ flip
+            for (int t = lane; t < (P >> 1); t += 32) {
+                // t-th pair of this step: i has bit j clear
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i ^ flip;
+                if (l < m) {                                    // i < l always; beyond m: +inf, nothing to do
+                    const double ka = key[i], kb = key[l];
+                    const int32_t ia = idx[i], ib = idx[l];
+                    if (kb < ka || (kb == ka && ib < ia)) {
+                        key[i] = kb;
+                        key[l] = ka;
+                        idx[i] = ib;
+                        idx[l] = ia;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+constexpr int SORT_SMEM = 512;   // pairs per warp sorted in shared memory; longer lists use the scratch
 
 // Kernel A (one warp per read): run-length view, per-run statistics, filtered pairs sorted by
 // state value, repeat-region borders.
@@ -357,20 +392,23 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
         }
 
         if (!SECOND && !fail) {
-            // ---- stable sort by state value (caller.py:306): rank sort ------------------------------
-            for (int i0 = 0; i0 < m; i0 += 32) {
-                const int i = i0 + lane;
-                if (i < m) {
-                    const double key = sc.px[i];
-                    int rank = 0;
-                    for (int j = 0; j < m; ++j) {
-                        const double o = sc.px[j];
-                        rank += (o < key) || (o == key && j < i);
-                    }
-                    sc.sx[rank] = key;
-                    sc.sy[rank] = sc.py[i];
-                }
+            // ---- stable sort by state value (caller.py:306) -----------------------------------------
+            __shared__ double s_key[4][SORT_SMEM];
+            __shared__ int32_t s_idx[4][SORT_SMEM];
+            const bool in_smem = m <= SORT_SMEM;
+            double *key = in_smem ? s_key[threadIdx.x >> 5] : sc.sx;
+            int32_t *idx = in_smem ? s_idx[threadIdx.x >> 5] : sc.sidx;
+            for (int i = lane; i < m; i += 32) {
+                key[i] = sc.px[i];
+                idx[i] = i;
             }
+            __syncwarp();
+            warp_sort_pairs(key, idx, m, lane);
+            for (int i = lane; i < m; i += 32) {
+                sc.sx[i] = key[i];
+                sc.sy[i] = sc.py[idx[i]];
+            }
+            __syncwarp();
         }
 
         // ---- repeat-region borders (caller.py:381-406) -------------------------------------------
@@ -591,6 +629,6 @@ int64_t wstr_mid_scratch_bytes(int T, int mv) {
     const int64_t R = T / (mv > 2 ? mv - 1 : 1) + 16;
     int64_t b = ((8 * R + 4 + 7) / 8) * 8;   // run_start (R+1) + run_state (R), int32
     b += 5 * 8 * R;                           // sv, px, py, sx, sy
-    b += R;                                   // good
+    b += 4 * R;                               // sidx
     return (b + 255) / 256 * 256;
 }
