@@ -1,3 +1,5 @@
+"""Step-time jitter of four ways to run the bench batch (whole batch resident, chunked resident, copy then
+chunks, the pipelined call_arrays), 20 steps each, synchronising after every step."""
 import os, sys, time, gc
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,6 @@
+"""Per-chunk timeline of CallerEngine.call_arrays (H2D / call / D2H events) over 30 steps; prints the step
+times with the library's kernel-time categories and the timelines of steps slower than 135 ms.  This is the
+script that showed cudaMemGetInfo and copy-engine-queued memsets stalling the pipeline."""
 import os, sys, time, gc
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,6 @@
 // Which companion instructions slow a DADD-dominated stream on sm_100a?  Per "state": 5 DADD + 1 DSETP
 // (FP64 pipe, 12 cycles) plus a variable set of ALU / FMA-pipe / LSU instructions.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o <name> <name>.cu ; run on a B200.
 #include <cstdio>
 #include <cuda_runtime.h>
 #define N_ITER 2048

@@ -1,4 +1,5 @@
 // Which part of the per-state instruction set costs FP64 issue rate on sm_100a?
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o <name> <name>.cu ; run on a B200.
 #include <cstdio>
 #include <cuda_runtime.h>
 #define N_ITER 2048
