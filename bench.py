@@ -354,8 +354,11 @@ def main():
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'CallerEngine.call_arrays (pinned host signal -> wstr_call_batch -> host arrays)',
                     'ms_each_step': per_step},
-            'gpu_launches': int(fill['launches'] + 3 * (mid['launches'] // 2) + 2 * (mid['launches'] - mid['launches'] // 2)
-                                + 2 * args.steps),
+            # this library's kernels inside the timed region: per fill launch one zero_kernel (its wave's work
+            # counters); per call 5 mid-stage kernels (3 after the first pass, 2 after the second), their 2
+            # zero_kernels and the upload_kernel of the host plan
+            'gpu_launches': int(2 * fill['launches'] + 3 * (mid['launches'] // 2) + 2 * (mid['launches'] - mid['launches'] // 2)
+                                + 3 * args.steps),
             'kernel_ms_per_step': {'dp_fill_traceback': fill['ms'] / args.steps, 'midstage': mid['ms'] / args.steps},
             'roofline': {'bound': 'fp64_add_pipe', 'achieved': achieved, 'peak': fp64_rate, 'unit': 'T FP64 add-class op/s',
                          'frac': achieved / fp64_rate, 'traffic': traffic,
