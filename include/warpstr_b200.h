@@ -87,7 +87,8 @@ int wstr_automaton_create(const double *values, const int32_t *seq_idx, const in
                           int32_t min_values_per_state, wstr_automaton **out);
 int wstr_automaton_destroy(wstr_automaton *a);
 /* Host-only dry run of the kernel layout (no device needed): info[0]=chain slots per lane (KC),
- * info[1]=generic slots per lane (KG), info[2]=in-degree the generic slots are unrolled for,
+ * info[1]=generic slots per lane (KG), info[2]=candidates the generic slots are unrolled for (2 or 4;
+ * 100+d: one for every generic slot but the last, d for the last),
  * info[3]=lanes holding chains, info[4]=states placed in generic slots; state_of_pos (optional)
  * receives the state at each of the 32*(KC+KG) positions, -1 = padding. */
 int wstr_automaton_plan(const int32_t *in_ptr, const int32_t *in_idx, int32_t n_states,

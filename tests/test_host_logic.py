@@ -97,7 +97,14 @@ def test_kernel_layout_plan_invariants(built_lib):
             assert sorted(int(s) for s in sop if s >= 0) == list(range(sta.n_states))
             pos = {int(s): p for p, s in enumerate(sop) if s >= 0}
             deg = np.diff(sta.in_ptr)
-            assert deg.max() <= info['unrolled_in_degree']
+            code = info['unrolled_in_degree']           # 2 / 4, or 100 + d for the "low" layout
+            low, dmax = code >= 100, code % 100
+            assert deg.max() <= dmax
+            if low:                                     # only the last generic slot takes fan-in
+                for s_, p_ in pos.items():
+                    u_ = p_ % K
+                    if KC <= u_ < K - 1:
+                        assert deg[s_] <= 1
             outdeg = np.bincount(sta.in_idx, minlength=sta.n_states)
             for s, p in pos.items():
                 lane, u = divmod(p, K)

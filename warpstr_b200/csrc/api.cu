@@ -235,17 +235,35 @@ int build_layout(int S, const int32_t *in_ptr, const int32_t *in_idx, int mv, La
     }
     L.n_lanes = lane;
     std::sort(generic.begin(), generic.end());
+    // "low" layout (dtw.cu: DegOf): when the generic states with more than one incoming edge fit
+    // the last generic slot, all other generic slots are built with a single candidate
+    std::vector<int> multi, single;
+    for (int g : generic) (c.indeg[g] > 1 ? multi : single).push_back(g);
+    const bool low = L.KG >= 2 && mv == 4 && (int)multi.size() <= 32 &&
+                     (int)single.size() <= 32 * (L.KG - 1) + (32 - (int)multi.size());
+    if (low) {
+        // singles fill slots 0..KG-2 and then the free lanes of the last slot, in state order
+        generic.clear();
+        const int head = std::min<int>((int)single.size(), 32 * (L.KG - 1));
+        generic.insert(generic.end(), single.begin(), single.begin() + head);
+        generic.resize(32 * (L.KG - 1), -1);
+        generic.insert(generic.end(), multi.begin(), multi.end());
+        generic.insert(generic.end(), single.begin() + head, single.end());
+    }
     int max_indeg = 0;
+    int placed = 0;
     for (size_t gi = 0; gi < generic.size(); ++gi) {
+        if (generic[gi] < 0) continue;
         const int g = (int)gi / 32, ln = (int)gi % 32;
         const int pos = ln * K + L.KC + g;
         L.state_of_pos[pos] = generic[gi];
         L.pos_of_state[generic[gi]] = pos;
         max_indeg = std::max(max_indeg, c.indeg[generic[gi]]);
+        ++placed;
     }
-    L.n_generic = (int)generic.size();
+    L.n_generic = placed;
     if (max_indeg > WSTR_MAX_DEG) return WSTR_ERR_UNSUPPORTED;
-    L.DEG = max_indeg <= 2 ? 2 : 4;
+    L.DEG = (max_indeg <= 2 ? 2 : 4) + (low ? 100 : 0);
     return WSTR_OK;
 }
 
@@ -371,7 +389,10 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     d.KC = KC;
     d.KG = KG;
     d.DEG = L.DEG;
-    d.NB = KC + KG * L.DEG;          // direction bits per lane and row (dtw.cu: DirFmt)
+    {                                // direction bits per lane and row (dtw.cu: DirFmt)
+        const int dmax = L.DEG >= 100 ? L.DEG - 100 : L.DEG;
+        d.NB = L.DEG >= 100 ? KC + (KG - 1) + dmax : KC + KG * dmax;
+    }
     d.RPW = 32 / d.NB;
     d.S = S;
     d.end_pos = L.pos_of_state[endstate];

@@ -118,13 +118,29 @@ __host__ __device__ constexpr int q_row_len() { return 32 * KG + 40; }
 
 // Direction codes.  Per cell a small mask of the candidates that took the lead in turn (bit r =
 // incoming edge r, tried in list order, so the winner is the highest set bit; 0 = stay): one
-// bit for a chain slot, DEG bits for a generic slot, NB = KC + KG*DEG bits per lane and row.
+// bit for a chain slot, one bit per candidate of a generic slot, NB bits per lane and row.
 // RPW = 32/NB consecutive rows share one 32-bit word per lane (row i: word i/RPW, bit field
 // (i%RPW)*NB); a word row [32 lanes] is one coalesced 128-byte line.  HD/FMR1/C9orf72 (6,2,2):
 // 10 bits, 3 rows per word = 0.17 B per cell.
+// DEG encodes the candidates per generic slot: 2 or 4 = that many for every slot; 100 + d =
+// "low" layout, one candidate for every generic slot but the last, d for the last (the host
+// puts the states with more than one incoming edge there).
+template <int DEG>
+struct DegOf {
+    static constexpr bool LOW = DEG >= 100;
+    static constexpr int MAX = LOW ? DEG - 100 : DEG;
+};
+template <int KG, int DEG>
+__host__ __device__ constexpr int slot_deg(int g) {
+    return (DegOf<DEG>::LOW && g < KG - 1) ? 1 : DegOf<DEG>::MAX;
+}
+template <int KC, int KG, int DEG>
+__host__ __device__ constexpr int slot_bit(int g) {      // first bit of generic slot g in a row's field
+    return DegOf<DEG>::LOW ? KC + g : KC + g * DegOf<DEG>::MAX;
+}
 template <int KC, int KG, int DEG>
 struct DirFmt {
-    static constexpr int NB = KC + KG * DEG;
+    static constexpr int NB = slot_bit<KC, KG, DEG>(KG - 1) + DegOf<DEG>::MAX;
     static constexpr int RPW = 32 / NB;
     static_assert(NB <= 32 && RPW >= 1, "direction codes of one row must fit a 32-bit word");
 };
@@ -195,7 +211,7 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
         s.D[k] = best;
     }
 
-    // ---- generic slots: stay, then up to DEG incoming edges in list order --------------------
+    // ---- generic slots: stay, then the slot's incoming edges in list order ------------------------
 #pragma unroll
     for (int g = 0; g < KG; ++g) {
         const int k = KC + g;
@@ -203,14 +219,16 @@ __device__ __forceinline__ void dp_row(LaneState<KC + KG, MV> &s, const LaneCons
         const double stay = s.D[k] + ae;
         double best = stay;
 #pragma unroll
-        for (int r = 0; r < DEG; ++r) {
-            const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
-            best = take_min(best, codes, Qrow[idx] + ae, 1u << (B0 + KC + g * DEG + r));
+        for (int r = 0; r < DegOf<DEG>::MAX; ++r) {
+            if (r < slot_deg<KG, DEG>(g)) {
+                const uint32_t idx = (lc.gsrc[g] >> (8 * r)) & 0xffu;
+                best = take_min(best, codes, Qrow[idx] + ae, 1u << (B0 + slot_bit<KC, KG, DEG>(g) + r));
+            }
         }
         if (BAND) {
             if ((lc.band_bits >> k) & 1u) {
                 best = INF;
-                codes &= ~(((1u << DEG) - 1u) << (B0 + KC + g * DEG));
+                codes &= ~(((1u << slot_deg<KG, DEG>(g)) - 1u) << (B0 + slot_bit<KC, KG, DEG>(g)));
             }
         }
         advance<K, MV, PH>(s, k, ae, stay);
@@ -430,7 +448,14 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
                 uint32_t nib = 0u;
                 if (coded && row <= i) {
                     const uint32_t f = wslot[hl] >> fsh;
-                    nib = u < KC ? (f >> u) & 1u : (f >> (KC + (u - KC) * DEG)) & ((1u << DEG) - 1u);
+                    if (u < KC) {
+                        nib = (f >> u) & 1u;
+                    } else {
+                        const int g = u - KC;
+                        const bool one = DegOf<DEG>::LOW && g < KG - 1;
+                        const int off = DegOf<DEG>::LOW ? KC + g : KC + g * DegOf<DEG>::MAX;
+                        nib = (f >> off) & (one ? 1u : (1u << DegOf<DEG>::MAX) - 1u);
+                    }
                 }
                 const uint32_t moves = __ballot_sync(FULL, nib != 0u);
                 if (moves == 0u) {                          // stays down to the window's last row
@@ -442,7 +467,7 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
                 const uint32_t nibm = __shfl_sync(FULL, nib, tm);
                 const int back = mv - static_cast<int>(__shfl_sync(FULL, mb, tm));
                 const int code = 31 - __clz(nibm);          // last candidate that took the lead
-                const int32_t pp = spred[pos * DEG + code];
+                const int32_t pp = spred[pos * DegOf<DEG>::MAX + code];
                 if (rm < back || pp < 0) {
                     failed = true;
                     break;
@@ -478,7 +503,7 @@ struct alignas(16) FillSmem {
     double sig[2][CH];                   // look-ahead reads may run up to 2*(mv-1) samples past a tile (into Q: unused)
     double Q[MV - 1][q_row_len<KG>()];   // one published buffer per pipeline phase
     uint32_t win[G::WORDS];              // traceback windows
-    int32_t pred[(KC + KG) * 32 * DEG];  // traceback: (state << 16 | position) of the predecessor, by position and code
+    int32_t pred[(KC + KG) * 32 * DegOf<DEG>::MAX];  // traceback: (state << 16 | position) of the predecessor, by position and code
     uint64_t bar[2];                     // signal tiles
     uint64_t tbar[G::NBUF];              // traceback windows
 };
@@ -540,8 +565,9 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
 #pragma unroll
             for (int g = 0; g < KG; ++g) lc.gsrc[g] = __ldg(A->lane_tab + lane * WSTR_LANE_TAB_STRIDE + 2 + g);
             v0 = __ldg(A->v_pos + A->init_pos[0]);
-            for (int e = lane; e < K * 32 * DEG; e += 32)
-                sm.pred[e] = __ldg(A->pred_tab + (e / DEG) * WSTR_PRED_STRIDE + 1 + (e % DEG));
+            constexpr int DM = DegOf<DEG>::MAX;
+            for (int e = lane; e < K * 32 * DM; e += 32)
+                sm.pred[e] = __ldg(A->pred_tab + (e / DM) * WSTR_PRED_STRIDE + 1 + (e % DM));
             cached_aut = m.aut;
         }
 
@@ -670,15 +696,19 @@ int launch_fill_t(const FillParams &p, cudaStream_t s) {
 
 template <int KC, int KG, int MV>
 int launch_fill_deg(int deg, const FillParams &p, cudaStream_t s) {
-    if (deg <= 2) return launch_fill_t<KC, KG, 2, MV>(p, s);
-    return launch_fill_t<KC, KG, 4, MV>(p, s);
+    if (deg == 2) return launch_fill_t<KC, KG, 2, MV>(p, s);
+    if (deg == 4) return launch_fill_t<KC, KG, 4, MV>(p, s);
+    if constexpr (KG >= 2 && MV == 4) {     // low layouts: one candidate for all generic slots but the last
+        if (deg == 102) return launch_fill_t<KC, KG, 102, MV>(p, s);
+        if (deg == 104) return launch_fill_t<KC, KG, 104, MV>(p, s);
+    }
+    return WSTR_ERR_UNSUPPORTED;
 }
 
 }  // namespace
 
 // the (chain, generic) slot splits the library is built with; keep in sync with kSplits in api.cu
 int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
-    if (deg > 4) return WSTR_ERR_UNSUPPORTED;
 #define WSTR_CASE(KC_, KG_, MV_) \
     if (kc == KC_ && kg == KG_ && mv == MV_) return launch_fill_deg<KC_, KG_, MV_>(deg, p, s);
     WSTR_CASE(7, 1, 4)
