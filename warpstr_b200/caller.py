@@ -102,6 +102,7 @@ class CallerEngine:
         self.timeline = None      # set to a list to collect (label, CUDA event) pairs from call_arrays
         self._host_out = None
         self._dev_cache = {}
+        self._h2d_probe = None
 
     # -- automata ------------------------------------------------------------------------
     def add_automaton(self, sta, flank_length: int) -> int:
@@ -255,13 +256,7 @@ class CallerEngine:
         off = np.asarray(off, dtype=np.int64)
         aut = np.asarray(aut, dtype=np.int32)
         rev = np.asarray(rev, dtype=np.uint8)
-        # chunk boundaries: a short first chunk (its copy is the only one nothing overlaps), then
-        # doubling up to chunk_reads
-        step = max(1, chunk_reads)
-        bounds, size = [0], max(1, step // 16)
-        while bounds[-1] < n:
-            bounds.append(min(n, bounds[-1] + size))
-            size = min(step, size * 2)
+        bounds = self._chunk_bounds(n, max(1, chunk_reads))
         cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
         seq_off = np.zeros(n + 1, dtype=np.int64)
         seq_off[1:] = np.cumsum(cap)
@@ -308,7 +303,12 @@ class CallerEngine:
             # every chunk's copy is queued up front (the calls stage their metadata through a
             # kernel, so nothing of theirs waits behind these copies on the DMA engine); the
             # host only has to keep the compute stream fed
+            h2d_begin = torch.cuda.Event(enable_timing=True)
+            h2d_begin.record(cs_in)
             sent = [send(a, b) for a, b in chunks]
+            h2d_end = torch.cuda.Event(enable_timing=True)
+            h2d_end.record(cs_in)
+            self._h2d_probe = (h2d_begin, h2d_end, int(d_sig.numel()) * 8)
             for ci, (a, b) in enumerate(chunks):
                 lo, hi, ev = sent[ci]
                 comp.wait_event(ev)
@@ -341,6 +341,43 @@ class CallerEngine:
             res['seq2'] = out['seq2'][:int(seq_off[-1])].numpy()
             res['seq_off'] = seq_off[:-1]
         return res
+
+    def _chunk_bounds(self, n: int, step: int):
+        """Chunk boundaries of the end-to-end pipeline.  The first chunk is short (its copy is the
+        only one nothing overlaps) and sizes double from there.  When the host link keeps well
+        ahead of the kernels (one GPU per host link: ~55 GB/s measured) they double up to ``step``;
+        when the previous call's copies ran slower (several GPUs sharing the host's memory
+        system) chunks stay small and shrink again at the end, because then the time after the last
+        copy -- one chunk's worth of kernels -- is what is exposed."""
+        slow_link = False
+        probe = self._h2d_probe
+        if probe is not None and probe[1].query():
+            ms = probe[0].elapsed_time(probe[1])
+            slow_link = ms > 0 and probe[2] / ms / 1e6 < 40.0        # GB/s
+        first = max(1, step // 16)
+        if not slow_link:
+            bounds, size = [0], first
+            while bounds[-1] < n:
+                bounds.append(min(n, bounds[-1] + size))
+                size = min(step, size * 2)
+            return bounds
+        cap = max(first, step // 4)
+        up, size, used = [], first, 0
+        while size < cap and used + 2 * size <= n:                     # mirrored ramps at both ends
+            up.append(size)
+            used += 2 * size
+            size *= 2
+        mid = n - used
+        sizes = list(up)
+        while mid > 0:
+            take = min(cap, mid)
+            sizes.append(take)
+            mid -= take
+        sizes += up[::-1]
+        bounds = [0]
+        for sz in sizes:
+            bounds.append(bounds[-1] + sz)
+        return bounds
 
     def _device_buffer(self, name: str, numel: int, dtype):
         import torch
