@@ -24,13 +24,20 @@ def v_resident_whole():
     eng.call_packed(d_sig, off, lengths, aut, rev)
 def v_e2e():
     eng.call_arrays(host, off, lengths, aut, rev)
+def v_e2e2():
+    eng.call_arrays(host, off, lengths, aut, rev, lanes=2)
+def v_e2e2s():
+    eng.call_arrays(host, off, lengths, aut, rev, lanes=2, chunk_reads=25000)
 def v_h2d_then_chunks():
     d_sig.copy_(host, non_blocking=True)
     v_resident_chunks()
 gc.collect(); gc.disable()
-for name, fn in (('resident whole', v_resident_whole), ('resident chunks', v_resident_chunks), ('h2d then chunks', v_h2d_then_chunks), ('e2e', v_e2e)):
+def v3(): eng.call_arrays(host, off, lengths, aut, rev, lanes=3, chunk_reads=25000)
+def v2c(): eng.call_arrays(host, off, lengths, aut, rev, lanes=2, chunk_reads=12500)
+def v3c(): eng.call_arrays(host, off, lengths, aut, rev, lanes=3, chunk_reads=12500)
+for name, fn in (('3 lanes 25000', v3), ('2 lanes 12500', v2c), ('3 lanes 12500', v3c), ('e2e', v_e2e), ('e2e 2 lanes', v_e2e2), ('e2e 2 lanes, chunks to 25000', v_e2e2s)):
     for _ in range(3): fn()
     ts = []
-    for rep in range(20):
+    for rep in range(10):
         torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); ts.append(round((time.perf_counter() - t0) * 1e3, 1))
     print(name, ts)

@@ -69,3 +69,37 @@ def test_gather_records_two_ranks_gloo():
         p.join(timeout=30)
     assert all(ok for _, ok, _ in res)
     assert sum(n for _, _, n in res) == n_total
+
+
+def test_chunk_schedule_of_the_pipelined_call():
+    """CallerEngine.call_arrays: chunk sizes ramp up from a short first chunk; when the previous
+    call's copies were slow the chunks stay small and shrink again at the end."""
+    from warpstr_b200.caller import CallerEngine
+
+    class Probe:
+        def __init__(self, ms):
+            self.ms = ms
+
+        def query(self):
+            return True
+
+        def elapsed_time(self, other):
+            return other.ms
+
+    class Stub:
+        _h2d_probe = None
+
+    for n in (0, 1, 10, 3125, 7000, 100000, 123457):
+        for probe in (None, (Probe(0), Probe(48.0), 2650306272), (Probe(0), Probe(100.0), 2650306272)):
+            e = Stub()
+            e._h2d_probe = probe
+            b = CallerEngine._chunk_bounds(e, n, 25000)
+            assert b[0] == 0 and b[-1] == n
+            sizes = np.diff(b)
+            assert (sizes > 0).all() and sizes.sum() == n
+            if n >= 100000:
+                assert sizes[0] == 3125                       # the only copy nothing overlaps is short
+                if probe is not None and probe[1].ms > 66:    # < 40 GB/s: small, mirrored chunks
+                    assert sizes.max() <= 12500 and sizes[-1] <= 6250
+                else:
+                    assert sizes.max() == 25000

@@ -98,6 +98,8 @@ class CallerEngine:
         self.tables: List[dict] = []
         self._ws = None
         self._ws_at_limit = False
+        self._lane_ws = {}
+        self._lane_streams = None
         self._copy_stream = None
         self.timeline = None      # set to a list to collect (label, CUDA event) pairs from call_arrays
         self._host_out = None
@@ -119,7 +121,19 @@ class CallerEngine:
         return len(self.automata) - 1
 
     # -- device helpers ---------------------------------------------------------------------
-    def _workspace(self, need: int):
+    def _workspace(self, need: int, lane: int = 0):
+        if lane:
+            # extra compute lanes of the pipelined call own a workspace each (sized for their chunks)
+            ws = self._lane_ws.get(lane)
+            if ws is None or ws.numel() < need:
+                import torch
+                self._lane_ws[lane] = None
+                ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self._lane_ws[lane] = ws
+            return ws
+        return self._workspace0(need)
+
+    def _workspace0(self, need: int):
         """Device workspace of ``need`` bytes, or as much as the memory limit allows (the library
         then works in waves).  The buffer only grows; cudaMemGetInfo is asked only when it has
         to (the call can block for tens of milliseconds while the GPU is busy)."""
@@ -204,14 +218,14 @@ class CallerEngine:
         return d_sig, off, lengths, np.asarray(aut_ids, dtype=np.int32), np.asarray(reverse, dtype=np.uint8)
 
     def call_packed(self, d_sig, off, lengths, aut, rev, want_seq: bool = True, want_debug: bool = False,
-                    into: Optional[dict] = None):
+                    into: Optional[dict] = None, lane: int = 0):
         """wstr_call_batch on device-resident signals.  Returns a dict of device tensors
         (len1, len2, cost1, cost2, status[, seq1, seq2, seq_off])."""
         import torch
         n = len(lengths)
         with torch.cuda.device(self.device):
             need = _lib.call_workspace_bytes(self.automata, aut, lengths)
-            ws = self._workspace(need)
+            ws = self._workspace(need, lane)
             if into is not None:      # caller-owned result buffers (views of the right sizes)
                 o = dict(into)
                 o['status'].zero_()
@@ -244,12 +258,13 @@ class CallerEngine:
         return o
 
     def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True,
-                    chunk_reads: int = 50000) -> Dict[str, np.ndarray]:
+                    chunk_reads: int = 25000, lanes: int = 2) -> Dict[str, np.ndarray]:
         """Array-level end-to-end call: (pinned) host signal buffer in, host arrays out --
         len1 ('orig'), len2 ('results'), cost1, cost2, status and, optionally, the decoded
-        sequence bytes.  The batch is cut into chunks of ``chunk_reads`` reads; one copy stream
-        moves chunk i+1 to the device and another brings chunk i-1's results back while the
-        compute stream works on chunk i.  ``call_batch`` wraps this into ``CallerResult`` objects."""
+        sequence bytes.  The batch is cut into chunks of up to ``chunk_reads`` reads; one copy
+        stream moves the chunks to the device, another brings results back, and the calls
+        alternate between ``lanes`` compute streams so that one chunk's kernel tails and
+        mid-stage overlap the next chunk's DP.  ``call_batch`` wraps this into ``CallerResult`` objects."""
         import torch
         n = len(lengths)
         lengths = np.asarray(lengths, dtype=np.int32)
@@ -309,19 +324,31 @@ class CallerEngine:
             h2d_end = torch.cuda.Event(enable_timing=True)
             h2d_end.record(cs_in)
             self._h2d_probe = (h2d_begin, h2d_end, int(d_sig.numel()) * 8)
+            # chunks alternate between `lanes` compute streams (each with its own workspace): the
+            # kernels of consecutive chunks are independent, so one chunk's kernel tails and
+            # latency-bound mid-stage overlap the next chunk's DP
+            n_lanes = max(1, int(lanes))
+            if n_lanes > 1 and self._lane_streams is None:
+                self._lane_streams = [torch.cuda.Stream() for _ in range(3)]
+            streams = [comp] + (self._lane_streams[:n_lanes - 1] if n_lanes > 1 else [])
+            for st in streams[1:]:
+                st.wait_stream(comp)
             for ci, (a, b) in enumerate(chunks):
                 lo, hi, ev = sent[ci]
-                comp.wait_event(ev)
-                mark(f'call{a} begin', comp)
-                into = {k: dev[k][a:b] for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
-                if want_seq:
-                    into['seq1'] = dev['seq1'][int(seq_off[a]):int(seq_off[b])]
-                    into['seq2'] = dev['seq2'][int(seq_off[a]):int(seq_off[b])]
-                o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b], want_seq=want_seq,
-                                     into=into)
-                mark(f'call{a} end', comp)
-                done = torch.cuda.Event()
-                done.record(comp)
+                lane = ci % len(streams)
+                st = streams[lane]
+                with torch.cuda.stream(st):
+                    st.wait_event(ev)
+                    mark(f'call{a} begin', st)
+                    into = {k: dev[k][a:b] for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+                    if want_seq:
+                        into['seq1'] = dev['seq1'][int(seq_off[a]):int(seq_off[b])]
+                        into['seq2'] = dev['seq2'][int(seq_off[a]):int(seq_off[b])]
+                    o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b],
+                                         want_seq=want_seq, into=into, lane=lane)
+                    mark(f'call{a} end', st)
+                    done = torch.cuda.Event()
+                    done.record(st)
                 with torch.cuda.stream(cs_out):                 # results back while the next chunk computes
                     cs_out.wait_event(done)
                     for k in ('len1', 'len2', 'cost1', 'cost2', 'status'):
@@ -332,6 +359,8 @@ class CallerEngine:
                         out['seq2'][s0:s1].copy_(o['seq2'][:s1 - s0], non_blocking=True)
                     mark(f'd2h{a} end', cs_out)
                 keep.append(o)
+            for st in streams[1:]:
+                comp.wait_stream(st)
             cs_out.synchronize()
             comp.wait_stream(cs_in)
             comp.wait_stream(cs_out)
@@ -354,14 +383,14 @@ class CallerEngine:
         if probe is not None and probe[1].query():
             ms = probe[0].elapsed_time(probe[1])
             slow_link = ms > 0 and probe[2] / ms / 1e6 < 40.0        # GB/s
-        first = max(1, step // 16)
+        first = max(1, step // 8)
         if not slow_link:
             bounds, size = [0], first
             while bounds[-1] < n:
                 bounds.append(min(n, bounds[-1] + size))
                 size = min(step, size * 2)
             return bounds
-        cap = max(first, step // 4)
+        cap = max(first, step // 2)
         up, size, used = [], first, 0
         while size < cap and used + 2 * size <= n:                     # mirrored ramps at both ends
             up.append(size)
