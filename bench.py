@@ -326,9 +326,11 @@ def main():
                 traffic = tj.get('dram_bytes_per_launch_at_bench_size') * (args.reads / waves) / tj.get('reads', 100000)
             except Exception:
                 traffic = None
-        # FP64-pipe instructions the kernel executes per DP row of one read (32 lanes x 8 slots; HD layout
-        # 6 chain + 2 generic slots, in-degree 2): DADD 5 per chain slot, 6 per generic; DSETP 1 per candidate
-        fp64_per_row = 32 * ((5 * 6 + 6 * 2) + (6 + 2 * 2))
+        # FP64-pipe instructions the kernel executes per DP row of one read: per lane 5 DADD per chain slot,
+        # 4 + candidates per generic slot, one DSETP per candidate = 4 K + 2 NB (K slots per lane, NB = direction
+        # bits per lane and row = candidates), times 32 lanes
+        inf = [eng.automata[i].info() for i in ids]
+        fp64_per_row = float(np.mean([32 * (4 * a['states_per_lane'] + 2 * a['dir_bits_per_row']) for a in inf]))
         rows_pass = float(lengths.astype(np.int64).sum())
         secs = fill_ms_launch * 1e-3
         hbm_peak = None
