@@ -25,7 +25,7 @@ def _run(cc, rc, name='HD', n=6, seed=70, noise=0.2, flank=110, engine=None):
     return res, want
 
 
-@pytest.mark.parametrize('mv', [3, 4, 5])
+@pytest.mark.parametrize('mv', [2, 3, 4, 5, 6])
 def test_min_values_per_state(built_lib, oracle_c, mv):
     res, want = _run(CallerConfig(min_values_per_state=mv), RescalerConfig())
     for g, w in zip(res, want):

@@ -714,8 +714,10 @@ int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaS
     WSTR_CASE(7, 1, 4)
     WSTR_CASE(6, 2, 4)
     WSTR_CASE(8, 1, 4)
+    WSTR_CASE(6, 2, 2)
     WSTR_CASE(6, 2, 3)
     WSTR_CASE(6, 2, 5)
+    WSTR_CASE(6, 2, 6)
     WSTR_CASE(4, 4, 4)
     WSTR_CASE(8, 2, 4)
     WSTR_CASE(6, 4, 4)
