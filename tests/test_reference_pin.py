@@ -63,3 +63,26 @@ def test_normalize_oracle_against_reference(ref):
     raw = rng.integers(200, 1100, size=5001).astype(np.int16)
     assert np.array_equal(no.brute_remove(raw), ref.Fast5.brute_remove(raw))
     assert np.array_equal(no.normalize_signal_mad(raw), ref.normalize_signal_mad(raw))
+
+
+def test_bundled_reads_against_reference_run(ref):
+    """Two of the reference's own bundled test reads (real nanopore signal, golden/c1_bundled.npz):
+    the unmodified reference's normalisation and WarpSTR.run against what the fixture holds from
+    the oracle -- which is what the GPU path is compared with in tests/test_gpu_c1.py."""
+    import os
+    from warpstr_b200 import templates as tmpl
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'c1_bundled.npz'))
+    left, right, seq, F = str(z['left']), str(z['right']), str(z['sequence']), int(z['flank_length'])
+    regex = {False: left + seq + right,
+             True: tmpl.reverse_complement(right) + tmpl.reverse_uniq_sequence(seq) + tmpl.reverse_complement(left)}
+    order = np.argsort(z['r_end_raw'] - z['l_start_raw'])[:2]            # the two shortest windows
+    for i in order:
+        raw = np.cumsum(z[f'raw_delta{i}'].astype(np.int64)).astype(np.int16)
+        norm = ref.normalize_signal_mad(ref.Fast5.brute_remove(raw))       # Fast5.get_data_processed, fast5.py:45-57
+        x = np.ascontiguousarray(norm[int(z['l_start_raw'][i]):int(z['r_end_raw'][i]) + 1])
+        rev = bool(z['reverse'][i])
+        sta = ref.StateAutomata(regex[rev])
+        got = ref.WarpSTR(F, sta.states, sta.endstate, sta.mask, None, rev, str(z['names'][i])).run(x)
+        assert got.seq == str(z['seq'][i]) and got.resc_seq == str(z['resc_seq'][i])
+        assert got.cost == z['cost1'][i] and got.resc_cost == z['cost2'][i]
+        assert len(got.resc_seq) in (40, 44)
