@@ -77,6 +77,69 @@ def test_normalisation_window_clipping_and_many_reads(built_lib):
     assert np.array_equal(get_data_processed(raws[0]), no.get_data_processed(raws[0], (0, len(raws[0]) - 1)))
 
 
+@pytest.mark.parametrize('mode', ['None', 'Brute', 'median3', 'median5'])
+def test_normalisation_edges(built_lib, mode):
+    """Reads of every small length (all eight alignments of the first sample inside a 16-byte
+    vector, reads shorter than a tile, tile-boundary lengths), spikes on the first / last samples
+    and across tile boundaries, out-of-histogram values, clipped and empty windows."""
+    from oracle import normalize_oracle as no
+    from warpstr_b200.normalize import normalize_windows
+    rng = np.random.default_rng(int.from_bytes(mode.encode(), 'little') % 1000)
+    lens = list(range(1, 40)) + [2047, 2048, 2049, 4095, 4096, 4097, 6143, 6150] + \
+        [int(v) for v in rng.integers(40, 7000, size=60)]
+    raws, wins = [], []
+    for n in lens:
+        r = rng.integers(300, 900, size=n).astype(np.int16)
+        for pos in (0, 1, 2, 3, n - 3, n - 2, n - 1, 2046, 2047, 2048, 2049, 4095, 4096):
+            if 0 <= pos < n and rng.random() < 0.6:
+                r[pos] = rng.choice([1500, 100, 1001, 249, 20000, -700])
+        if n > 50 and rng.random() < 0.5:                      # a run of adjacent spikes
+            a = int(rng.integers(3, n - 10))
+            r[a:a + 4] = 1800
+        raws.append(r)
+        lo = int(rng.integers(0, n))
+        wins.append((lo, int(rng.integers(lo - 1 if lo else 0, 2 * n))))
+    got = normalize_windows(raws, wins, mode)
+    for r, w, g in zip(raws, wins, got):
+        want = no.get_data_processed(r, w, mode)
+        assert g.shape == want.shape, (len(r), w)
+        assert np.array_equal(g, want, equal_nan=True), (len(r), w, mode)
+
+
+def test_pore_lookup_edges(built_lib):
+    """Every length around the 4-outputs-per-thread grouping, invalid characters at every offset,
+    an output buffer that is not 16-byte aligned."""
+    import torch
+    from warpstr_b200 import _lib
+    from warpstr_b200.pore_model import get_pore_model
+    pm = get_pore_model()
+    table = np.ascontiguousarray(pm.table)
+    d_tab = torch.from_numpy(table).cuda()
+    rng = np.random.default_rng(12)
+    code = {c: i for i, c in enumerate('ACGT')}
+    for n in list(range(6, 40)) + [1023, 1024, 1029, 5000]:
+        seq = ''.join(rng.choice(list('ACGT'), size=n))
+        for bad_at in (None, 0, 3, n - 1, n // 2):
+            s = seq if bad_at is None else seq[:bad_at] + 'N' + seq[bad_at + 1:]
+            want = np.full(n - 5, np.nan)
+            for i in range(n - 5):
+                kmer = s[i:i + 6]
+                if 'N' not in kmer:
+                    idx = 0
+                    for ch in kmer:
+                        idx = idx * 4 + code[ch]
+                    want[i] = table[idx]
+            d_seq = torch.from_numpy(np.frombuffer(s.encode(), dtype=np.uint8).copy()).cuda()
+            for shift in (0, 1):                               # shift 1: output not 16-byte aligned
+                buf = torch.full((n - 5 + 2,), -1.0, dtype=torch.float64, device='cuda')
+                d_bad = torch.zeros(1, dtype=torch.int32, device='cuda')
+                _lib.pore_lookup(d_seq, d_tab, 6, buf[shift:shift + n - 5], d_bad)
+                got = buf.cpu().numpy()
+                assert np.array_equal(got[shift:shift + n - 5], want, equal_nan=True), (n, bad_at, shift)
+                assert got[shift + n - 5] == -1.0 and (shift == 0 or got[0] == -1.0)
+                assert int(d_bad.item()) == int(np.isnan(want).sum())
+
+
 def test_pore_lookup_matches_reference_golden(built_lib):
     from warpstr_b200.pore_model import get_pore_model
     sq = np.load(os.path.join(GOLD, 'squiggle.npz'))
