@@ -32,10 +32,8 @@ def v_h2d_then_chunks():
     d_sig.copy_(host, non_blocking=True)
     v_resident_chunks()
 gc.collect(); gc.disable()
-def v3(): eng.call_arrays(host, off, lengths, aut, rev, lanes=3, chunk_reads=25000)
-def v2c(): eng.call_arrays(host, off, lengths, aut, rev, lanes=2, chunk_reads=12500)
-def v3c(): eng.call_arrays(host, off, lengths, aut, rev, lanes=3, chunk_reads=12500)
-for name, fn in (('3 lanes 25000', v3), ('2 lanes 12500', v2c), ('3 lanes 12500', v3c), ('e2e', v_e2e), ('e2e 2 lanes', v_e2e2), ('e2e 2 lanes, chunks to 25000', v_e2e2s)):
+def v1(): eng.call_arrays(host, off, lengths, aut, rev, lanes=1, chunk_reads=50000)
+for name, fn in (('resident whole', v_resident_whole), ('resident chunks', v_resident_chunks), ('e2e 1 lane, chunks to 50000', v1), ('e2e', v_e2e), ('e2e 2 lanes', v_e2e2), ('e2e 2 lanes, chunks to 25000', v_e2e2s)):
     for _ in range(3): fn()
     ts = []
     for rep in range(10):
