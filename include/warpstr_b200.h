@@ -141,7 +141,7 @@ typedef struct {
     int32_t states_in_segment;      /* tr_calling_config.states_in_segment */
     double threshold;               /* rescaling.threshold */
     double max_std;                 /* rescaling.max_std */
-    int32_t method;                 /* rescaling.method: 0 mean; 1 median is WSTR_ERR_UNSUPPORTED here */
+    int32_t method;                 /* rescaling.method: 0 mean, 1 median */
     int32_t reps_as_one;            /* rescaling.reps_as_one: must be 0 here */
 } wstr_call_params;
 

@@ -57,9 +57,18 @@ def test_spline_with_interior_knots_goes_to_the_host(built_lib, oracle_c):
         assert g.resc_cost == pytest.approx(w.resc_cost, rel=1e-9)
 
 
-@pytest.mark.parametrize('rc', [RescalerConfig(method='median'), RescalerConfig(reps_as_one=True)])
-def test_host_engine_variants(built_lib, oracle_c, rc):
-    res, want = _run(CallerConfig(), rc, n=3)
+@pytest.mark.parametrize('name', ['HD', 'DM2'])
+def test_median_method_on_the_device(built_lib, oracle_c, name):
+    """rescaling.method 'median': the run's state value is np.median of its samples."""
+    res, want = _run(CallerConfig(), RescalerConfig(method='median'), name=name, n=8, noise=0.25)
+    for g, w in zip(res, want):
+        assert g.seq == w.seq and g.resc_seq == w.resc_seq
+        assert g.cost == w.cost and g.resc_cost == w.resc_cost
+
+
+@pytest.mark.parametrize('rc,engine', [(RescalerConfig(method='median'), 'host'), (RescalerConfig(reps_as_one=True), None)])
+def test_host_engine_variants(built_lib, oracle_c, rc, engine):
+    res, want = _run(CallerConfig(), rc, n=3, engine=engine)
     for g, w in zip(res, want):
         assert g.seq == w.seq and g.resc_seq == w.resc_seq
         assert g.resc_cost == pytest.approx(w.resc_cost, rel=1e-9)

@@ -199,14 +199,14 @@ class CallerEngine:
         """WarpSTR.run for a batch (caller.py:117-149).  ``engine='gpu'`` (default for the
         default rescaling configuration) keeps everything on the device (wstr_call_batch);
         ``engine='host'`` runs the two DP passes on the GPU and the stage between them in
-        numpy/scipy (needed for ``reps_as_one`` / ``method: median``)."""
+        numpy/scipy (needed for ``reps_as_one``)."""
         signals = [np.ascontiguousarray(s, dtype=np.float64) for s in signals]
-        gpu_ok = (not self.rc.reps_as_one) and self.rc.method == 'mean'
+        gpu_ok = not self.rc.reps_as_one
         engine = engine or ('gpu' if gpu_ok else 'host')
         if engine == 'host':
             return self._call_batch_host(signals, aut_ids, reverse)
         if not gpu_ok:
-            raise _lib.WarpstrError('the device mid-stage covers reps_as_one=False, method=mean only')
+            raise _lib.WarpstrError('the device mid-stage covers reps_as_one=False only')
         res = self.call_packed(*self.upload(signals, aut_ids, reverse))
         return self.results_from(res, signals, aut_ids, reverse)
 
@@ -251,7 +251,8 @@ class CallerEngine:
                 o['trace2'] = torch.empty(d_sig.numel(), dtype=torch.int32, device=self.device)
                 o['rescaled'] = torch.empty(d_sig.numel(), dtype=torch.float64, device=self.device)
             params = _lib.CallParams(self.cc.min_values_per_state, self.cc.states_in_segment,
-                                     float(self.rc.threshold), float(self.rc.max_std), 0, 0)
+                                     float(self.rc.threshold), float(self.rc.max_std),
+                                     1 if self.rc.method == 'median' else 0, 0)
             _lib.call_batch(self.automata, aut, rev, d_sig, off, lengths, params, ws, o['len1'], o['len2'],
                             o['cost1'], o['cost2'], o['status'], o.get('seq1'), o.get('seq2'), seq_off,
                             o.get('trace1'), o.get('trace2'), o.get('rescaled'))

@@ -833,7 +833,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
         return WSTR_ERR_INVALID_ARGUMENT;
     if ((out->d_seq1 || out->d_seq2) && !out->seq_off) return WSTR_ERR_INVALID_ARGUMENT;
     if (n_reads == 0) return WSTR_OK;
-    if (params->method != 0 || params->reps_as_one != 0) return WSTR_ERR_UNSUPPORTED;
+    if ((params->method != 0 && params->method != 1) || params->reps_as_one != 0) return WSTR_ERR_UNSUPPORTED;
     if (params->states_in_segment < 2) return WSTR_ERR_INVALID_ARGUMENT;
     const int mv = automata[0]->dev.mv;
     if (params->min_values_per_state != mv) return WSTR_ERR_INVALID_ARGUMENT;
@@ -924,6 +924,8 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     mp.status = out->d_status;
     mp.mv = mv;
     mp.sis = params->states_in_segment;
+    mp.method = params->method;
+    mp.pad_ = 0;
     mp.threshold = params->threshold;
     mp.max_std = params->max_std;
     if (int zrc = zero_counters(d_queue, 64, s)) return zrc;

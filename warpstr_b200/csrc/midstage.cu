@@ -257,6 +257,24 @@ __device__ __forceinline__ uint8_t complement(uint8_t b) {
     }
 }
 
+// np.median of a run (caller.py:323-325, rescaling.method 'median'): the middle order statistic,
+// or the mean of the two middle ones; runs are short (a state's dwell), so ranks are counted
+__device__ double run_median(const double *xs, int n) {
+    const int k_lo = (n - 1) / 2, k_hi = n / 2;
+    double v_lo = 0.0, v_hi = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double xi = xs[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const double xj = xs[j];
+            rank += (xj < xi) || (xj == xi && j < i);
+        }
+        if (rank == k_lo) v_lo = xi;
+        if (rank == k_hi) v_hi = xi;
+    }
+    return (n & 1) ? v_hi : (v_lo + v_hi) / 2.0;
+}
+
 struct Scratch {
     int32_t *run_start, *run_state;
     double *sv, *px, *py, *sx, *sy;
@@ -367,11 +385,13 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
                     const double sum = pairwise_sum([xs](int i) { return xs[i]; }, 0, n);
                     mean = sum / (double)n;
                     expect = A.values[run_state[r]];
+                    const double avg = mean;                       // np.std is taken about the mean either way
+                    if (p.method == 1) mean = run_median(xs, n);   // 'mean' is the run's state value from here on
                     sc.sv[r] = mean;
                     if (n >= p.mv) {
                         const double ss = pairwise_sum(
-                            [xs, mean](int i) {
-                                const double d = xs[i] - mean;
+                            [xs, avg](int i) {
+                                const double d = xs[i] - avg;
                                 return d * d;
                             },
                             0, n);

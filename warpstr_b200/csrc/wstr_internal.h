@@ -102,6 +102,7 @@ struct MidParams {
     uint8_t *seq;                // may be NULL
     int32_t *status;
     int32_t mv, sis;
+    int32_t method, pad_;        // 0 mean, 1 median (state value of a run)
     double threshold, max_std;
 };
 
