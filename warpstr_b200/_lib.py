@@ -6,7 +6,7 @@ shared library is missing, or a call fails, this module raises.
 """
 import ctypes
 import os
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import numpy as np
 

@@ -7,7 +7,7 @@ both passes run in the CUDA kernels behind ``wstr_warp_batch``; :class:`CallerEn
 batches reads so that thousands of them are in flight at once.
 """
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 

@@ -12,8 +12,6 @@ rescaler configurations the GPU mid-stage does not cover (``reps_as_one``,
 ``method: median``, splines that need interior knots).
 """
 from dataclasses import dataclass
-from math import sqrt
-from typing import List, Optional, Tuple
 
 import numpy as np
 from scipy import interpolate

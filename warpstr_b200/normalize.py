@@ -2,10 +2,10 @@
 
 Mirrors the numerics of the reference's ``Fast5.get_data_processed`` / ``remove_spikes`` /
 ``normalize_signal_mad`` (schemas/fast5.py:45-57, 68-77, 90-114) for raw int16 reads that are
-already in memory; reading the fast5 container itself is outside this path.  All reads of a
+already in memory (``fast5.py`` reads them from the fast5 container).  All reads of a
 batch are processed by one launch of ``wstr_normalize_batch``.
 """
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 

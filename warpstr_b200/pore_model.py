@@ -11,7 +11,7 @@ SURVEY Appendix C last paragraph).
 """
 import os
 import re
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, Iterable, Optional, Tuple
 
 import numpy as np
 

@@ -8,7 +8,7 @@ units the caller works in.  Reverse-strand reads realise the reverse-complemente
 sequence, which is what the reverse automaton (wrapper.py:72-84) expects.
 """
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
