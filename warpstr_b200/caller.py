@@ -465,6 +465,13 @@ class CallerEngine:
         return out
 
     def _call_batch_host(self, signals, aut_ids, reverse) -> List[CallerResult]:
+        """Both DP passes on the GPU, the stage between them with the reference's own numpy/scipy
+        calls on the host.  Never silent: used for ``reps_as_one``, for reads whose smoothing spline
+        needs interior knots (impossible at the default thresholds) and to raise the reference's
+        exception for a read the device flagged."""
+        import warnings
+        warnings.warn(f'warpstr_b200: {len(signals)} read(s) take the host mid-stage (scipy splrep/splev); '
+                      'the DP passes still run on the GPU', RuntimeWarning, stacklevel=3)
         traces1 = self.warp_batch(signals, aut_ids)
         first = []
         for s, a, t in zip(signals, aut_ids, traces1):
