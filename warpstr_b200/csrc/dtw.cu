@@ -155,6 +155,9 @@ struct DirOut {
 // min(best, cand) with the reference's strict '<'; when cand wins, OR `bit` into codes.
 // (The result is a fresh register on purpose: tying it to `best` would force a copy whenever
 // best is still needed, as the stay value is for the pipeline.)
+// (Comparing the bit patterns as unsigned integers instead -- legal, every value is a
+// non-negative sum or +inf -- moves the compare off the FP64 pipe but costs two to four ISETP
+// on the ALU pipe, which the selects and code bits already load: no gain, SASS checked.)
 __device__ __forceinline__ double take_min(const double best, uint32_t &codes, const double cand, const uint32_t bit) {
     double out;
     asm("{\n"
@@ -514,15 +517,19 @@ struct alignas(16) FillSmem {
 #ifdef WSTR_MAXNREG
 #define WSTR_FILL_BOUNDS __maxnreg__(WSTR_MAXNREG)
 #else
-#define WSTR_FILL_BOUNDS \
-    __launch_bounds__(32 * WSTR_WARPS_PER_CTA, (KC + KG <= 9 ? WSTR_K8_BLOCKS : (KC + KG <= 12 ? 3 : 2)))
+// resident warps per SM: 4 * WSTR_K8_BLOCKS (12: 168 registers per thread) up to 12 states per lane, 8 beyond
+#define WSTR_FILL_BOUNDS                         \
+    __launch_bounds__(32 * WSTR_WARPS_PER_CTA,   \
+                      (KC + KG <= 9 ? 4 * WSTR_K8_BLOCKS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
 #endif
 template <int KC, int KG, int DEG, int MV>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int K = KC + KG;
     constexpr int NB = DirFmt<KC, KG, DEG>::NB, RPW = DirFmt<KC, KG, DEG>::RPW;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (one-warp CTAs: say so outright, so that every shared-memory address below is a constant)
+    const int warp = WSTR_WARPS_PER_CTA == 1 ? 0 : static_cast<int>(threadIdx.x >> 5);
+    const int lane = WSTR_WARPS_PER_CTA == 1 ? static_cast<int>(threadIdx.x) : static_cast<int>(threadIdx.x & 31);
     using Smem = FillSmem<KC, KG, DEG, MV>;
     Smem &sm = reinterpret_cast<Smem *>(smem_raw)[warp];
     const double INF = dinf();
@@ -543,7 +550,10 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
     int cached_aut = -1;
     double v0 = 0.0;
 
-    for (;;) {
+    // (a counted loop on purpose -- no warp can take more than p.n reads: with `for (;;)` ptxas emits
+    // the row loops a third longer, 297 instead of 262 instructions per 3-row cycle, and does not
+    // fold the shared-memory addresses; checked in the SASS)
+    for (int taken = 0; taken < p.n; ++taken) {
         int r = 0;
         if (lane == 0) r = atomicAdd(p.queue, 1);
         r = __shfl_sync(FULL, r, 0);

@@ -95,20 +95,69 @@ __device__ double pairwise_sum(const F &f, int start0, int n0) {
     return ret;
 }
 
+// ---- exact division by a divisor that is used many times -------------------------------------------
+// The spline basis divides by (xe - xb) six times per evaluated sample and the t statistic by 3.0
+// five times per position; a double division is ~15 FP64-pipe instructions on this GPU.  With
+// y = RN(1/d) taken once (one IEEE division),
+//     q0 = RN(a*y);  r0 = a - q0*d (exact, one FMA);  q1 = RN(q0 + r0*y);
+//     r1 = a - q1*d (exact);                          q  = RN(q1 + r1*y)
+// is the correctly rounded a/d (Markstein 1990: one such step on a faithful q with a correctly
+// rounded reciprocal rounds correctly; the first step makes q1 faithful), i.e. the very bits
+// `a / d` gives, in 5 instructions.  Used only where nothing can over- or underflow (|d| and |a|
+// within 2^+-100 and 2^+-400); every other operand takes the plain division.  The identity was
+// also checked on the host against a/d for 4e9 operand pairs, adversarial significands included
+// (divisor all-ones / power of two / 1.5): no mismatch.
+struct Divisor {
+    double d, y;
+    bool fast;     // 2^-60 <= |d| <= 2^60
+};
+__device__ __forceinline__ Divisor make_divisor(double d) {
+    Divisor r;
+    r.d = d;
+    r.y = 1.0 / d;
+    const unsigned e = (static_cast<unsigned>(__double2hiint(d)) >> 20) & 0x7ffu;
+    r.fast = e - (1023u - 60u) <= 120u;
+    return r;
+}
+// the five-instruction form; the caller vouches for the operand ranges
+__device__ __forceinline__ double div_fast(double a, const Divisor &dv) {
+    const double q0 = __dmul_rn(a, dv.y);
+    const double r0 = __fma_rn(-q0, dv.d, a);
+    const double q1 = __fma_rn(r0, dv.y, q0);
+    const double r1 = __fma_rn(-q1, dv.d, a);
+    return __fma_rn(r1, dv.y, q1);
+}
+// GUARD: test the numerator (and the divisor's flag) per call; otherwise the caller has
+// established that every numerator is 0 or within 2^+-600
+template <bool GUARD>
+__device__ __forceinline__ double div_exact(double a, const Divisor &dv) {
+    if (!GUARD) return div_fast(a, dv);
+    const unsigned e = (static_cast<unsigned>(__double2hiint(a)) >> 20) & 0x7ffu;
+    if (dv.fast && e - (1023u - 400u) <= 800u) return div_fast(a, dv);
+    return a / dv.d;
+}
+// 0, or 2^-120 <= |v| <= 2^120: sums, differences and triple products of such values (and of
+// quotients by a `fast` divisor) stay far inside the range div_fast needs
+__device__ __forceinline__ bool tame(double v) {
+    const unsigned hi = static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu;
+    return (hi >> 20) - (1023u - 120u) <= 240u || (hi | static_cast<unsigned>(__double2loint(v))) == 0u;
+}
+
 // ---- FITPACK pieces for the single-interval cubic ------------------------------------------------
-// fpbspl with k=3 on knots [xb,xb,xb,xb,xe,xe,xe,xe], interval l=4
-__device__ __forceinline__ void bspl3(double xb, double xe, double x, double *h) {
+// fpbspl with k=3 on knots [xb,xb,xb,xb,xe,xe,xe,xe], interval l=4; span = make_divisor(xe - xb)
+template <bool GUARD>
+__device__ __forceinline__ void bspl3(double xb, double xe, const Divisor &span, double x, double *h) {
     double hh[3];
     h[0] = 1.0;
     for (int j = 1; j <= 3; ++j) {
         for (int i = 0; i < j; ++i) hh[i] = h[i];
         h[0] = 0.0;
         for (int i = 1; i <= j; ++i) {
-            if (xe == xb) {
+            if (GUARD && xe == xb) {   // (an unguarded caller has a non-zero span)
                 h[i] = 0.0;
                 continue;
             }
-            const double f = hh[i - 1] / (xe - xb);
+            const double f = div_exact<GUARD>(hh[i - 1], span);
             h[i - 1] = h[i - 1] + f * (xe - x);
             h[i] = f * (x - xb);
         }
@@ -143,6 +192,7 @@ struct Cubic {
 // least-squares cubic through (sx[i], sy[i]), i < m, sx ascending: fpcurf's first iteration
 __device__ void lsq_cubic(const double *sx, const double *sy, int m, Cubic &out) {
     const double xb = sx[0], xe = sx[m - 1];
+    const Divisor span = make_divisor(xe - xb);
     double a[4][4], z[4];
     for (int i = 0; i < 4; ++i) {
         z[i] = 0.0;
@@ -153,7 +203,7 @@ __device__ void lsq_cubic(const double *sx, const double *sy, int m, Cubic &out)
         const double xi = sx[it];
         double yi = sy[it];
         double h[4];
-        bspl3(xb, xe, xi, h);
+        bspl3<true>(xb, xe, span, xi, h);
         for (int i = 0; i < 4; ++i) {
             const double piv = h[i];
             if (piv == 0.0) continue;
@@ -190,38 +240,56 @@ __device__ void lsq_cubic(const double *sx, const double *sy, int m, Cubic &out)
     for (int q = 0; q < 4; ++q) out.c[q] = c[q];
 }
 
-__device__ __forceinline__ double splev3(const Cubic &cu, double x) {
+template <bool GUARD>
+__device__ __forceinline__ double splev3(const Cubic &cu, const Divisor &span, double x) {
     double h[4];
-    bspl3(cu.xb, cu.xe, x, h);
+    bspl3<GUARD>(cu.xb, cu.xe, span, x, h);
     double sp = 0.0;
     for (int j = 0; j < 4; ++j) sp = sp + cu.c[j] * h[j];
     return sp;
 }
 
 // ---- sliding two-sample statistic (caller.py:347-354), windows x[c-3:c] and x[c:c+3] -----------
-__device__ __forceinline__ void mean_sd3(const double *w, double &mean, double &sd) {
-    mean = ((w[0] + w[1]) + w[2]) / 3.0;
+template <bool GUARD>
+__device__ __forceinline__ void mean_sd3(const double *w, const Divisor &three, double &mean, double &sd) {
+    mean = div_exact<GUARD>((w[0] + w[1]) + w[2], three);
     const double d0 = w[0] - mean, d1 = w[1] - mean, d2 = w[2] - mean;
-    const double var = ((d0 * d0 + d1 * d1) + d2 * d2) / 3.0;
+    const double var = div_exact<GUARD>((d0 * d0 + d1 * d1) + d2 * d2, three);
     sd = sqrt(var);
 }
 
-__device__ __forceinline__ double tstat(const double *x, int c) {
-    double ma, sa, mb, sb;
-    mean_sd3(x + c - 3, ma, sa);
-    mean_sd3(x + c, mb, sb);
-    double sd = sqrt((sa * sa + sb * sb) / 3.0);
+template <bool GUARD>
+__device__ __forceinline__ double tstat_of(double ma, double sa, double mb, double sb, const Divisor &three) {
+    double sd = sqrt(div_exact<GUARD>(sa * sa + sb * sb, three));
     if (sd == 0.0) sd = sd + 0.0000001;
     return (ma - mb) / sd;
 }
 
-// number of detected segment borders minus one in t(c0..c1) (caller.py:357-378)
-__device__ int count_segments(const double *x, int c0, int c1) {
+// number of detected segment borders minus one in t(c0..c1) (caller.py:357-378).  t(c) compares
+// x[c-3:c] with x[c:c+3]; the right window of position c is the left window of c+3, so its mean
+// and deviation are kept for three positions instead of being computed twice.
+// GUARD = false: every sample of the read is `tame`, the divisions by 3 need no range test.
+template <bool GUARD>
+__device__ int count_segments(const double *__restrict__ x, int c0, int c1) {
+    const Divisor three = make_divisor(3.0);
     int borders = 0;
     bool rising = false;
-    double prev = tstat(x, c0);
+    double prev = 0.0;
+    double m0 = 0.0, s0 = 0.0, m1 = 0.0, s1 = 0.0, m2 = 0.0, s2 = 0.0;   // right windows of c-3, c-2, c-1
     for (int c = c0; c <= c1; ++c) {
-        const double t = c == c0 ? prev : tstat(x, c);
+        double ma, sa, mb, sb;
+        if (c - c0 >= 3) {
+            ma = m0;
+            sa = s0;
+        } else {
+            mean_sd3<GUARD>(x + c - 3, three, ma, sa);
+        }
+        mean_sd3<GUARD>(x + c, three, mb, sb);
+        m0 = m1; s0 = s1;
+        m1 = m2; s1 = s2;
+        m2 = mb; s2 = sb;
+        const double t = tstat_of<GUARD>(ma, sa, mb, sb, three);
+        if (c == c0) prev = t;
         if (t > 3.0 || t < -3.0) {
             if ((t > 3.0 && t >= prev) || (t < -3.0 && t <= prev)) {
                 rising = true;
@@ -349,24 +417,38 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
         int fail = 0;
 
         // ---- run-length view of the trace (caller.py:58-60) -----------------------------------
+        // (four trace words per lane are in flight before the first is looked at; the state of the
+        // sample before comes from the neighbouring lane, not from a second load)
         int n_runs = 0;
-        for (int t0 = 0; t0 < T; t0 += 32) {
-            const int t = t0 + lane;
-            bool head = false;
-            int st = 0;
-            if (t < T) {
-                st = trace[t];
-                head = t == 0 || trace[t - 1] != st;
-            }
-            const unsigned bal = __ballot_sync(FULL, head);
-            if (head) {
-                const int r = n_runs + __popc(bal & ((1u << lane) - 1u));
-                if (r < R) {
-                    run_start[r] = t;
-                    run_state[r] = st;
+        {
+            const int32_t *__restrict__ tr = trace;
+            int before = -1;                       // state of the sample in front of the current 32
+            for (int t0 = 0; t0 < T; t0 += 128) {
+                int sv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    sv[u] = t < T ? tr[t] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    const int st = sv[u];
+                    int left = __shfl_up_sync(FULL, st, 1);
+                    if (lane == 0) left = before;
+                    before = __shfl_sync(FULL, st, 31);
+                    const bool head = t < T && (t == 0 || left != st);
+                    const unsigned bal = __ballot_sync(FULL, head);
+                    if (head) {
+                        const int r = n_runs + __popc(bal & ((1u << lane) - 1u));
+                        if (r < R) {
+                            run_start[r] = t;
+                            run_state[r] = st;
+                        }
+                    }
+                    n_runs += __popc(bal);
                 }
             }
-            n_runs += __popc(bal);
         }
         if (n_runs > R) fail = WSTR_READ_SEGMENT;   // cannot happen: a run has >= mv-1 samples
         if (!fail && lane == 0) run_start[n_runs] = T;
@@ -554,8 +636,31 @@ __global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
             cu.c[2] = ci[4];
             cu.c[3] = ci[5];
             // ---- rescaled signal (caller.py:312) ------------------------------------------------
-            double *out = p.rescaled + rd.sig_off;
-            for (int t = lane; t < T; t += 32) out[t] = splev3(cu, x[t]);
+            // four samples per lane are fetched before the first is evaluated; a sample whose distances
+            // to both knots are tame takes the unguarded divisions (all of them, in practice)
+            double *__restrict__ out = p.rescaled + rd.sig_off;
+            const double *__restrict__ xr = x;
+            const Divisor span = make_divisor(cu.xe - cu.xb);
+            bool all_tame = true;
+            for (int t0 = 0; t0 < T; t0 += 128) {
+                double xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    xv[u] = t < T ? xr[t] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    if (t < T) {
+                        const double v = xv[u];
+                        all_tame = all_tame && tame(v);
+                        if (span.fast && tame(cu.xe - v) && tame(v - cu.xb)) out[t] = splev3<false>(cu, span, v);
+                        else out[t] = splev3<true>(cu, span, v);
+                    }
+                }
+            }
+            const bool tt_fast = __all_sync(FULL, all_tame);
             // ---- bad-repeat mask (caller.py:336-344, 409-421) -----------------------------------
             uint32_t *mw = p.maskbits + rd.mask_off;
             const int nwords = (T + 31) >> 5;
@@ -567,7 +672,8 @@ __global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
                     const int b_lo = run_start[ra + n * p.sis + 1] - 1;
                     const int b_hi = run_start[ra + (n + 1) * p.sis + 1] - 1;
                     const int c1 = min(b_hi, T - 3);
-                    if (count_segments(x, b_lo, c1) >= p.sis + 1) {
+                    const int segs = tt_fast ? count_segments<false>(x, b_lo, c1) : count_segments<true>(x, b_lo, c1);
+                    if (segs >= p.sis + 1) {
                         for (int w = b_lo >> 5; w <= (b_hi - 1) >> 5; ++w) {
                             const int lo = max(b_lo, w << 5), hi = min(b_hi, (w + 1) << 5);   // [lo, hi)
                             if (hi <= lo) continue;
