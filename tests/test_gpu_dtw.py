@@ -146,6 +146,43 @@ def test_device_call_intermediates_match_oracle(engine, oracle_c, name):
         assert res[n].cost == want.cost and res[n].resc_cost == want.resc_cost
 
 
+def test_untame_samples_take_the_guarded_divisions(engine, oracle_c):
+    """The mid-stage divides by repeated divisors with a 5-instruction exact sequence when the
+    operands are 'tame' (0 or within 2^+-120) and with the plain division otherwise.  Samples far
+    outside that range (tiny ones inside the read, huge ones at its end, where they cannot upset
+    the alignment) must give scipy's bits too: rescaled signal, both traces, costs."""
+    locus, stas, ids, reads = _setup(engine, 'HD', 4, seed=31, noise=0.2)
+    rng = np.random.default_rng(5)
+    sigs = []
+    for r in reads:
+        x = r.signal.copy()
+        idx = rng.integers(200, len(x) - 200, 12)
+        x[idx[:6]] = 2.0 ** -130
+        x[idx[6:9]] = -2.0 ** -140
+        x[idx[9:]] = 0.0
+        x[-1] = 2.0 ** 130
+        x[-2] = -2.0 ** 125
+        sigs.append(x)
+    aut = [ids[int(r.reverse)] for r in reads]
+    rev = [r.reverse for r in reads]
+    packed = engine.upload(sigs, aut, rev)
+    o = engine.call_packed(*packed, want_debug=True)
+    off, lengths = packed[1], packed[2]
+    assert not o['status'].cpu().numpy().any()
+    t1, t2, resc = o['trace1'].cpu().numpy(), o['trace2'].cpu().numpy(), o['rescaled'].cpu().numpy()
+    res = engine.results_from(o, sigs, aut, rev)
+    for n, r in enumerate(reads):
+        tb = co.tables_from(stas[int(r.reverse)])
+        want = co.run_read(sigs[n], tb, 110, r.reverse, impl='c')
+        a, ln = int(off[n]), int(lengths[n])
+        assert np.array_equal(t1[a:a + ln], want.trace1), n
+        assert np.array_equal(resc[a:a + ln], want.rescaled), n
+        assert np.array_equal(t2[a:a + ln], want.trace2), n
+        assert res[n].seq == want.seq and res[n].resc_seq == want.resc_seq
+        assert res[n].cost == want.cost and res[n].resc_cost == want.resc_cost
+        assert len(res[n].resc_seq) == r.truth_len
+
+
 def test_device_and_host_engines_agree(engine):
     locus, stas, ids, reads = _setup(engine, 'HD', 24, seed=29, noise=0.3)
     args = ([r.signal for r in reads], [ids[int(r.reverse)] for r in reads], [r.reverse for r in reads])

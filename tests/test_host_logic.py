@@ -160,3 +160,26 @@ def test_synthetic_batch_generator_is_consistent():
     again = synth.make_read_batch(locus, 50, seed=9)
     assert np.array_equal(sig, again[0]) and np.array_equal(lengths, again[2])
     assert (np.diff(off) >= lengths[:-1]).all()
+
+
+def test_exact_division_identity_the_midstage_relies_on(tmp_path):
+    """csrc/midstage.cu divides by repeated divisors with y = RN(1/d) and two FMA correction steps;
+    oracle/div_identity.c checks on the host that this gives the bits of a/d (random and adversarial
+    significands, the kernels' exponent ranges).  Needs gcc and a CPU with FMA."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    try:
+        if ' fma ' not in open('/proc/cpuinfo').read():
+            pytest.skip('host CPU has no FMA')
+    except OSError:
+        pytest.skip('cannot read /proc/cpuinfo')
+    exe = str(tmp_path / 'div_identity')
+    subprocess.check_call(['gcc', '-O2', '-mfma', '-ffp-contract=off', '-o', exe,
+                           os.path.join(root, 'oracle', 'div_identity.c'), '-lm'])
+    out = subprocess.run([exe, '5000000'], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert 'two_step_mismatches=0' in out.stdout
