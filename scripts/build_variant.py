@@ -17,9 +17,10 @@ for s in g.SOURCES:
     src = os.path.join(g.CSRC, s)
     obj = os.path.join(objdir, s + '.o')
     objs.append(obj)
-    # only dtw.cu depends on the experiment knobs; reuse the stock objects for the rest
+    # only dtw.cu (or aux.cu for the WSTR_NORM_* knobs) depends on the experiment knobs; reuse the stock objects for the rest
     stock = os.path.join(ROOT, 'build', s + '.o')
-    if s != 'dtw.cu' and os.path.exists(stock) and not any('WARPS_PER_CTA' in e for e in extra):
+    only_aux = any('WSTR_NORM' in e for e in extra)
+    if (s != ('aux.cu' if only_aux else 'dtw.cu')) and os.path.exists(stock) and not any('WARPS_PER_CTA' in e for e in extra):
         objs[-1] = stock
         continue
     procs.append(subprocess.Popen([g._nvcc()] + g.NVCC_FLAGS + extra + ['-c', src, '-o', obj]))

@@ -9,6 +9,7 @@
 //     than from a sort, and the float formulas follow numpy's (numpy 2.3
 //     lib/_function_base_impl.py: 'linear' virtual index (n-1)*q, _get_indexes, _lerp,
 //     median = mean of the middle one/two).  Compiled with -fmad=false.
+#include <limits.h>
 #include <math.h>
 
 #include "wstr_internal.h"
@@ -116,15 +117,16 @@ struct NormSmem {
     // tile[HALO + t] = sample t of the current tile; tile[HALO-2], tile[HALO-1] = the two
     // (patched) samples before it.  HALO = 8 keeps the tile 16-byte aligned for vector access.
     alignas(16) int16_t tile[TILE + 16];
-    uint16_t spikes[TILE];
-    int32_t warp_sums[NT / 32];
-    int32_t n_spikes;
+    uint32_t spike_bits[TILE / 32];  // Brute: out-of-range samples of the current tile (all zero between tiles)
     int32_t next_read;
     int32_t vmin, vmax;
     int32_t ghist_dirty;
     double shift, scale;
 };
 constexpr int HALO = 8;
+#ifndef WSTR_NORM_BLOCKS
+#define WSTR_NORM_BLOCKS 5          // resident CTAs per SM the register budget is set for (48 registers)
+#endif
 
 __device__ __forceinline__ uint32_t hcount(const NormSmem &sm, const uint32_t *gh, int v) {
     if (v >= 0 && v < HBINS) return sm.hist[v];
@@ -204,8 +206,9 @@ __device__ double absdev_at_rank(const NormSmem &sm, const uint32_t *gh, double 
 // 16-byte boundary at or before its first sample, so every thread loads its 8 samples with one
 // aligned 16-byte load, a tile ahead of their use (samples in front of / behind the read are
 // masked).  Per tile there is a single barrier unless the tile holds an out-of-range sample
-// (Brute) or a median filter is on.
-__global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
+// (Brute: two more, and only the threads that hold such a sample and one patching lane do any
+// work) or a median filter is on.  Indices inside a read are 32-bit.
+__global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const NormParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NormSmem &sm = *reinterpret_cast<NormSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -217,11 +220,12 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
         const int r = sm.next_read;
         if (r >= p.n_reads) break;
         const int16_t *raw = p.raw + p.raw_off[r];
-        const int64_t N = p.raw_off[r + 1] - p.raw_off[r];
-        const int64_t lo = p.win_lo[r], hi = p.win_hi[r];
-        const int64_t Tw = hi >= lo ? (min(hi, N - 1) - lo + 1) : 0;     // numpy slice semantics
+        // (a read has fewer than 2^31 - 2*TILE samples, checked by the host: tile-relative indices fit an int)
+        const int N = (int)(p.raw_off[r + 1] - p.raw_off[r]);
+        const int lo = p.win_lo[r], hi = p.win_hi[r];
+        const int Tw = hi >= lo ? max(min(hi, N - 1) - lo + 1, 0) : 0;   // numpy slice semantics
         double *out = p.out + p.out_off[r];
-        int16_t *stash = reinterpret_cast<int16_t *>(out) + 3 * Tw;      // tail of the output window
+        int16_t *stash = reinterpret_cast<int16_t *>(out) + 3 * (int64_t)Tw;   // tail of the output window
 
         for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
         if (tid == 0) {
@@ -230,28 +234,29 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
             sm.ghist_dirty = 0;
         }
         if (tid < HALO) sm.tile[tid] = 0;
+        if (tid < TILE / 32) sm.spike_bits[tid] = 0u;
         __syncthreads();
 
         // sample index g (0-based in the read) of tile k, thread tid, element u: k*TILE + tid*PER + u - mis
         const int mis = (int)((reinterpret_cast<uintptr_t>(raw) >> 1) & 7);
         const uint4 *vec = reinterpret_cast<const uint4 *>(raw - mis);
-        const int64_t n_tiles = (N + mis + TILE - 1) / TILE;
-        const int64_t n_vec = (N + mis + PER - 1) / PER;
-        auto fetch = [&](int64_t k) {
-            const int64_t v = k * NT + tid;
+        const int n_tiles = (N + mis + TILE - 1) / TILE;
+        const int n_vec = (N + mis + PER - 1) / PER;
+        auto fetch = [&](int k) {
+            const int v = k * NT + tid;
             return v < n_vec ? __ldg(vec + v) : make_uint4(0u, 0u, 0u, 0u);
         };
         uint4 nxt = fetch(0);
         int lmin = 32767, lmax = -32768;
-        for (int64_t k = 0; k < n_tiles; ++k) {
+        for (int k = 0; k < n_tiles; ++k) {
             union {
                 uint4 q;
                 int16_t h[PER];
             } cur;
             cur.q = nxt;
             if (k + 1 < n_tiles) nxt = fetch(k + 1);
-            const int64_t t_base = k * TILE - mis;                       // read index of tile element 0
-            const int64_t g0 = t_base + tid * PER;                       // ... of this thread's first sample
+            const int t_base = k * TILE - mis;                           // read index of tile element 0
+            const int g0 = t_base + tid * PER;                           // ... of this thread's first sample
             // block-uniform: every sample of the tile belongs to the read / the tile meets the window
             const bool interior = t_base >= 0 && t_base + TILE <= N;
             const bool in_window = t_base <= hi && t_base + TILE > lo;
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
                 tmax = -32768;
 #pragma unroll
                 for (int u = 0; u < PER; ++u) {
-                    const int64_t g = g0 + u;
+                    const int g = g0 + u;
                     if (g >= 0 && g < N) {
                         tmin = min(tmin, (int)cur.h[u]);
                         tmax = max(tmax, (int)cur.h[u]);
@@ -280,44 +285,46 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
             const bool slow = p.spike_mode == 1 ? __syncthreads_or(spike) != 0 : (__syncthreads(), p.spike_mode != 0);
 
             if (slow && p.spike_mode == 1) {
-                // Brute (fast5.py:90-101): ordered list of out-of-range samples of this tile ...
-                int cnt = 0;
-                bool flag[PER];
+                // Brute (fast5.py:90-101).  Only the threads that hold an out-of-range sample do
+                // anything: they mark their samples in a bitmap of the tile (a thread's 8 samples share
+                // one word) ...
+                if (spike) {
+                    uint32_t m = 0u;
 #pragma unroll
-                for (int u = 0; u < PER; ++u) {
-                    const int64_t g = g0 + u;
-                    flag[u] = g >= 0 && g < N && (cur.h[u] > 1000 || cur.h[u] < 250);
-                    cnt += flag[u];
+                    for (int u = 0; u < PER; ++u) {
+                        const int g = g0 + u;
+                        if (g >= 0 && g < N && (cur.h[u] > 1000 || cur.h[u] < 250)) m |= 1u << u;
+                    }
+                    if (m) atomicOr(&sm.spike_bits[tid >> 2], m << ((tid & 3) * PER));
                 }
-                int inc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                if (lane == 31) sm.warp_sums[warp] = inc;
                 __syncthreads();
-                int woff = 0;
-                for (int w = 0; w < warp; ++w) woff += sm.warp_sums[w];
-                int pos = woff + inc - cnt;
-#pragma unroll
-                for (int u = 0; u < PER; ++u)
-                    if (flag[u]) sm.spikes[pos++] = (uint16_t)(tid * PER + u);
-                if (tid == NT - 1) sm.n_spikes = woff + inc;
-                __syncthreads();
-                // ... patched one after the other: later medians see earlier fixes
-                if (tid == 0) {
-                    for (int s = 0; s < sm.n_spikes; ++s) {
-                        const int t = sm.spikes[s];
-                        const int64_t g = t_base + t;
-                        if (g > 2) {
-                            int16_t w5[5];
-                            const int n = (int)min((int64_t)5, N - (g - 2));
-                            for (int u = 0; u < n; ++u) {                // samples g-2 .. g-2+n-1
-                                const int e = t - 2 + u;                 // tile element (-2, -1 = carried)
-                                w5[u] = e < TILE ? sm.tile[HALO + e] : raw[g - 2 + u];   // not yet patched: raw
+                // ... and warp 0 walks the marked samples in ascending order, one lane patching them
+                // one after the other: later medians see earlier fixes
+                if (warp == 0) {
+                    for (int w0 = 0; w0 < TILE / 32; w0 += 32) {
+                        uint32_t word = sm.spike_bits[w0 + lane];
+                        if (word) sm.spike_bits[w0 + lane] = 0u;        // leave the bitmap clean
+                        unsigned live = __ballot_sync(0xffffffffu, word != 0u);
+                        while (live) {
+                            const int src = __ffs(live) - 1;
+                            live &= live - 1;
+                            uint32_t bits = __shfl_sync(0xffffffffu, word, src);
+                            if (lane == 0) {
+                                while (bits) {
+                                    const int t = (w0 + src) * 32 + (__ffs(bits) - 1);
+                                    bits &= bits - 1;
+                                    const int g = t_base + t;
+                                    if (g > 2) {
+                                        int16_t w5[5];
+                                        const int n = min(5, N - (g - 2));
+                                        for (int u = 0; u < n; ++u) {                // samples g-2 .. g-2+n-1
+                                            const int e = t - 2 + u;                 // tile element (-2, -1 = carried)
+                                            w5[u] = e < TILE ? sm.tile[HALO + e] : raw[g - 2 + u];   // not yet patched: raw
+                                        }
+                                        sm.tile[HALO + t] = median_small(w5, n);
+                                    }
+                                }
                             }
-                            sm.tile[HALO + t] = median_small(w5, n);
                         }
                     }
                 }
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
                     int16_t w5[5];
                     for (int d = -h; d <= h; ++d) {
                         const int e = tid * PER + u + d;
-                        const int64_t g = t_base + e;
+                        const int g = t_base + e;
                         int16_t vv = 0;
                         if (g >= 0 && g < N) vv = e < TILE ? sm.tile[HALO + e] : raw[g];
                         w5[d + h] = vv;
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
 #pragma unroll
                 for (int u = 0; u < PER; ++u) {
                     cur.h[u] = res[u];
-                    const int64_t g = g0 + u;
+                    const int g = g0 + u;
                     if (g >= 0 && g < N) {
                         tmin = min(tmin, (int)res[u]);
                         tmax = max(tmax, (int)res[u]);
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
             } else {
 #pragma unroll
                 for (int u = 0; u < PER; ++u) {
-                    const int64_t g = g0 + u;
+                    const int g = g0 + u;
                     if (g < 0 || g >= N) continue;
                     const int vv = cur.h[u];
                     if (vv >= 0 && vv < HBINS) {
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
             if (in_window) {
 #pragma unroll
                 for (int u = 0; u < PER; ++u) {
-                    const int64_t g = g0 + u;
+                    const int g = g0 + u;
                     if (g >= lo && g <= hi && g < N) stash[g - lo] = cur.h[u];
                 }
             }
@@ -454,7 +461,7 @@ __global__ void __launch_bounds__(NT) normalize_kernel(const NormParams p) {
 }
 
 int norm_grid(int n_reads) {
-    int g = 148 * 5;   // 5 CTAs per SM fit (41 KB of shared memory each)
+    int g = 148 * WSTR_NORM_BLOCKS;   // persistent: one CTA per resident slot (48 registers, 37 KB of shared memory each)
     return n_reads < g ? (n_reads < 1 ? 1 : n_reads) : g;
 }
 
@@ -475,8 +482,9 @@ extern "C" int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off
     if (spike_mode != 0 && spike_mode != 1 && spike_mode != 3 && spike_mode != 5) return WSTR_ERR_INVALID_ARGUMENT;
     if (n_reads == 0) return WSTR_OK;
     if (workspace_bytes < wstr_normalize_workspace_bytes(n_reads)) return WSTR_ERR_WORKSPACE_TOO_SMALL;
-    for (int r = 0; r < n_reads; ++r)
-        if (raw_off[r + 1] <= raw_off[r] || win_lo[r] < 0) return WSTR_ERR_INVALID_ARGUMENT;
+    for (int r = 0; r < n_reads; ++r)   // (the kernel indexes a read's samples with an int)
+        if (raw_off[r + 1] <= raw_off[r] || raw_off[r + 1] - raw_off[r] > (int64_t)INT32_MAX - 2 * TILE || win_lo[r] < 0)
+            return WSTR_ERR_INVALID_ARGUMENT;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     unsigned char *ws = static_cast<unsigned char *>(d_workspace);
     size_t off = 0;
