@@ -511,16 +511,22 @@ struct alignas(16) FillSmem {
     uint64_t tbar[G::NBUF];              // traceback windows
 };
 
-#ifndef WSTR_K8_BLOCKS
-#define WSTR_K8_BLOCKS 3
+// Resident warps per SM the register budget is set for, by states per lane.  Warps are bound to
+// one of the SM's four sub-partitions (16 K registers each): 12 warps = 3 per sub-partition =
+// 168 registers per thread, 13..16 warps = 4 per sub-partition = 128.  With one-warp CTAs the
+// (7,1) and (8,1) row loops fit 128 registers (no spill in the first-pass loop, one or two local
+// loads per 3-row cycle in the masked second-pass variants), and 16 warps are 2 % faster than 12.
+// The per-lane state is (KC+KG)*(MV+1) doubles; beyond 45 of them (min_values_per_state 5 or 6) the
+// loops would spill at 128 registers, so those keep the 12-warp budget.
+#ifndef WSTR_K8_WARPS
+#define WSTR_K8_WARPS 16
 #endif
 #ifdef WSTR_MAXNREG
 #define WSTR_FILL_BOUNDS __maxnreg__(WSTR_MAXNREG)
 #else
-// resident warps per SM: 4 * WSTR_K8_BLOCKS (12: 168 registers per thread) up to 12 states per lane, 8 beyond
 #define WSTR_FILL_BOUNDS                         \
     __launch_bounds__(32 * WSTR_WARPS_PER_CTA,   \
-                      (KC + KG <= 9 ? 4 * WSTR_K8_BLOCKS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
+                      ((KC + KG) * (MV + 1) <= 45 ? WSTR_K8_WARPS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
 #endif
 template <int KC, int KG, int DEG, int MV>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
@@ -688,6 +694,10 @@ int launch_fill_t(const FillParams &p, cudaStream_t s) {
     if (grid_cap == 0) {
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // (shared memory must not be what limits the resident warps: take the largest carve-out)
+        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
         int dev = 0, sms = 0, per_sm = 0;
         WSTR_CUDA(cudaGetDevice(&dev));
         WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
