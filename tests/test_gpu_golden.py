@@ -140,6 +140,41 @@ def test_pore_lookup_edges(built_lib):
                 assert int(d_bad.item()) == int(np.isnan(want).sum())
 
 
+def test_pore_lookup_long_sequences(built_lib):
+    """Sequences of 2^18 levels and more take the shared-memory-table kernel (8 levels per thread, 8-byte
+    base loads); same contract: invalid characters anywhere give NaN for every k-mer that holds them and
+    are counted, ragged ends, and unaligned inputs fall back to the plain kernel with the same result."""
+    import torch
+    from warpstr_b200 import _lib
+    from warpstr_b200.pore_model import get_pore_model
+    table = np.ascontiguousarray(get_pore_model().table)
+    d_tab = torch.from_numpy(table).cuda()
+    rng = np.random.default_rng(21)
+    for n in (262149, 300003, 524301):
+        codes = rng.integers(0, 4, n)
+        seq = np.frombuffer(b'ACGT', dtype=np.uint8)[codes].copy()
+        bad_at = np.array([0, 5, 6, 1000, 1001, 4095, 4096, n // 2, n - 12, n - 6, n - 1])
+        seq[bad_at] = np.frombuffer(b'NaNcgtN-NxN', dtype=np.uint8)
+        valid = np.ones(n, dtype=bool)
+        valid[bad_at] = False
+        idx = np.zeros(n - 5, dtype=np.int64)
+        ok = np.ones(n - 5, dtype=bool)
+        for p in range(6):
+            idx = idx * 4 + codes[p:p + n - 5]
+            ok &= valid[p:p + n - 5]
+        want = np.where(ok, table[idx], np.nan)
+        buf_seq = torch.zeros(n + 8, dtype=torch.uint8, device='cuda')
+        for s_shift, o_shift in ((0, 0), (1, 0), (0, 1)):
+            buf_seq[s_shift:s_shift + n] = torch.from_numpy(seq).cuda()
+            buf = torch.full((n - 5 + 2,), -1.0, dtype=torch.float64, device='cuda')
+            d_bad = torch.zeros(1, dtype=torch.int32, device='cuda')
+            _lib.pore_lookup(buf_seq[s_shift:s_shift + n], d_tab, 6, buf[o_shift:o_shift + n - 5], d_bad)
+            got = buf.cpu().numpy()
+            assert np.array_equal(got[o_shift:o_shift + n - 5], want, equal_nan=True), (n, s_shift, o_shift)
+            assert got[o_shift + n - 5] == -1.0 and (o_shift == 0 or got[0] == -1.0)
+            assert int(d_bad.item()) == int((~ok).sum())
+
+
 def test_pore_lookup_matches_reference_golden(built_lib):
     from warpstr_b200.pore_model import get_pore_model
     sq = np.load(os.path.join(GOLD, 'squiggle.npz'))

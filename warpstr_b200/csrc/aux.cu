@@ -71,12 +71,98 @@ __global__ void pore_lookup_kernel(const uint8_t *__restrict__ seq, int64_t n_ou
     }
 }
 
+// (2 bits, valid) of an upper-case base without branches: A 0, C 1, G 2, T 3
+__device__ __forceinline__ uint32_t base_code2(uint32_t c, bool &ok) {
+    ok = (c >> 5) == 2u && ((0x0010008Au >> (c & 31u)) & 1u);   // bits 1, 3, 7, 20 = 'A','C','G','T' - 64
+    const uint32_t t = (c >> 1) & 3u;                            // A 0, C 1, G 3, T 2
+    return t ^ (t >> 1);
+}
+
+// Long sequences (whole-panel expected signals): the table sits in shared memory -- a gather from L1
+// costs a tag look-up per distinct line, up to 32 per warp instruction for random k-mers, which is what
+// bounded the kernel above at 0.4 of the HBM rate -- every thread produces 8 consecutive levels from
+// 8 + k - 1 bases fetched with two 8-byte loads, and writes them with four 16-byte stores.
+// Needs k <= 6 (4^k doubles in shared memory), seq 8-byte and out 16-byte aligned.
+constexpr int PORE_VPT2 = 8;
+__global__ void __launch_bounds__(256) pore_lookup_smem_kernel(const uint8_t *__restrict__ seq, int64_t n_bases,
+                                                               int64_t n_out, const double *__restrict__ table, int k,
+                                                               int n_entries, double *__restrict__ out, int32_t *bad) {
+    extern __shared__ double pore_tab[];
+    for (int e = threadIdx.x; e < n_entries; e += blockDim.x) pore_tab[e] = table[e];
+    __syncthreads();
+    const uint32_t mask = (1u << (2 * k)) - 1u;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    int n_bad = 0;
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * PORE_VPT2; i < n_out;
+         i += (int64_t)gridDim.x * blockDim.x * PORE_VPT2) {
+        // bases i .. i+15: 8 of this thread's own and up to k-1 <= 7 of look-ahead
+        uint64_t w0 = 0, w1 = 0;
+        if (i + 16 <= n_bases) {
+            w0 = *reinterpret_cast<const uint64_t *>(seq + i);
+            w1 = *reinterpret_cast<const uint64_t *>(seq + i + 8);
+        } else {
+            for (int b = 0; b < 8; ++b) {
+                if (i + b < n_bases) w0 |= (uint64_t)seq[i + b] << (8 * b);
+                if (i + 8 + b < n_bases) w1 |= (uint64_t)seq[i + 8 + b] << (8 * b);
+            }
+        }
+        uint32_t idx = 0;
+        int valid = 0;                       // consecutive valid bases ending at the current one
+#pragma unroll
+        for (int p = 0; p < 7; ++p) {
+            if (p < k - 1) {
+                bool ok;
+                const uint32_t c = base_code2((uint32_t)(w0 >> (8 * p)) & 0xffu, ok);
+                idx = (idx << 2) | c;
+                valid = ok ? valid + 1 : 0;
+            }
+        }
+        double v[PORE_VPT2];
+#pragma unroll
+        for (int j = 0; j < PORE_VPT2; ++j) {
+            const int q = j + k - 1;         // position of the k-mer's last base relative to i (< 15)
+            const uint32_t ch = q < 8 ? (uint32_t)(w0 >> (8 * q)) & 0xffu : (uint32_t)(w1 >> (8 * (q - 8))) & 0xffu;
+            bool ok;
+            const uint32_t c = base_code2(ch, ok);
+            idx = ((idx << 2) | c) & mask;
+            valid = ok ? valid + 1 : 0;
+            v[j] = nan;
+            if (i + j < n_out) {
+                if (valid >= k) v[j] = pore_tab[idx];
+                else ++n_bad;
+            }
+        }
+        if (i + PORE_VPT2 <= n_out) {
+#pragma unroll
+            for (int j = 0; j < PORE_VPT2; j += 2)
+                reinterpret_cast<double2 *>(out + i)[j / 2] = make_double2(v[j], v[j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < PORE_VPT2; ++j)
+                if (i + j < n_out) out[i + j] = v[j];
+        }
+    }
+    if (n_bad && bad) atomicAdd(bad, n_bad);
+}
+
 extern "C" int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d_table, int32_t k, double *d_out,
                                 int32_t *d_bad, void *stream) {
     if (!d_seq || !d_table || !d_out || k < 1 || k > 15) return WSTR_ERR_INVALID_ARGUMENT;
     const int64_t n_out = n - k + 1;
     if (n_out <= 0) return WSTR_OK;
     const int threads = 256;
+    if (n_out >= (1 << 18) && k <= 6 && (reinterpret_cast<uintptr_t>(d_seq) & 7u) == 0 &&
+        (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0) {
+        const int n_entries = 1 << (2 * k);
+        int64_t blocks2 = (n_out + (int64_t)threads * PORE_VPT2 - 1) / ((int64_t)threads * PORE_VPT2);
+        if (blocks2 > 148 * 4) blocks2 = 148 * 4;
+        wstr_prof_begin(3, static_cast<cudaStream_t>(stream));
+        pore_lookup_smem_kernel<<<(int)blocks2, threads, n_entries * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
+            d_seq, n, n_out, d_table, k, n_entries, d_out, d_bad);
+        wstr_prof_end(static_cast<cudaStream_t>(stream));
+        WSTR_CUDA(cudaGetLastError());
+        return WSTR_OK;
+    }
     int64_t blocks = (n_out + (int64_t)threads * PORE_VPT - 1) / ((int64_t)threads * PORE_VPT);
     if (blocks > 148 * 16) blocks = 148 * 16;
     const int vec_ok = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
