@@ -345,12 +345,12 @@ __device__ __forceinline__ int mask_run_end(const uint32_t *__restrict__ mw, int
 }
 
 // rows [i0, i1) of one signal tile (all inside one band setting); mask bits pick SHORT rows
-template <int KC, int KG, int DEG, int MV, bool BAND>
+template <int KC, int KG, int DEG, int MV, bool BAND, bool MASKED>
 __device__ __forceinline__ void dp_tile_rows(LaneState<KC + KG, MV> &s, const LaneConsts<KG> &lc,
                                              const double *__restrict__ xs, const int tile0, int i0, const int i1,
                                              const uint32_t *__restrict__ mw_ptr, double *__restrict__ Qlane,
                                              const double *__restrict__ Qbase, DirOut &o) {
-    if (!mw_ptr) {
+    if (!MASKED || !mw_ptr) {
         dp_segment<KC, KG, DEG, MV, false, BAND>(s, lc, xs, tile0, i0, i1, Qlane, Qbase, o);
         return;
     }
@@ -517,7 +517,11 @@ struct alignas(16) FillSmem {
 // (7,1) and (8,1) row loops fit 128 registers (no spill in the first-pass loop, one or two local
 // loads per 3-row cycle in the masked second-pass variants), and 16 warps are 2 % faster than 12.
 // The per-lane state is (KC+KG)*(MV+1) doubles; beyond 45 of them (min_values_per_state 5 or 6) the
-// loops would spill at 128 registers, so those keep the 12-warp budget.
+// loops would spill at 128 registers, so those keep the 12-warp budget.  So does the MASKED
+// instantiation (second pass: rows whose mask bit is set allow the shorter dwell): its extra row
+// variants spill a few values per cycle at 128 registers, which costs what the fourth warp gains
+// (41.7 ms per pass either way).  The first-pass instantiation does not contain the masked variants
+// at all and has no local-memory access in its row loop.
 #ifndef WSTR_K8_WARPS
 #define WSTR_K8_WARPS 16
 #endif
@@ -526,9 +530,9 @@ struct alignas(16) FillSmem {
 #else
 #define WSTR_FILL_BOUNDS                         \
     __launch_bounds__(32 * WSTR_WARPS_PER_CTA,   \
-                      ((KC + KG) * (MV + 1) <= 45 ? WSTR_K8_WARPS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
+                      ((KC + KG) * (MV + 1) <= 45 && !MASKED ? WSTR_K8_WARPS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
 #endif
-template <int KC, int KG, int DEG, int MV>
+template <int KC, int KG, int DEG, int MV, bool MASKED>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int K = KC + KG;
@@ -635,7 +639,7 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
         // enters the skipped set from outside, its cells then stay +inf (and their codes 0) without
         // the per-cell test
         const int band_free = A->band_closed ? band_start + MV : T;
-        const uint32_t *mw_ptr = p.maskbits ? p.maskbits + m.mask_off : nullptr;
+        const uint32_t *mw_ptr = MASKED && p.maskbits ? p.maskbits + m.mask_off : nullptr;
         uint32_t *dir = p.dir + m.dir_off;
         DirOut o;   // rows below mv leave their bits 0
         o.acc = 0u;
@@ -663,8 +667,8 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
             for (int a = i_begin; a < i_end;) {
                 const bool banded = a >= band_start && a < band_free;
                 const int e = banded ? min(i_end, band_free) : (a < band_start ? min(i_end, band_start) : i_end);
-                if (banded) dp_tile_rows<KC, KG, DEG, MV, true>(s, lc, xs, c * CH, a, e, mw_ptr, Qlane, Qbase, o);
-                else dp_tile_rows<KC, KG, DEG, MV, false>(s, lc, xs, c * CH, a, e, mw_ptr, Qlane, Qbase, o);
+                if (banded) dp_tile_rows<KC, KG, DEG, MV, true, MASKED>(s, lc, xs, c * CH, a, e, mw_ptr, Qlane, Qbase, o);
+                else dp_tile_rows<KC, KG, DEG, MV, false, MASKED>(s, lc, xs, c * CH, a, e, mw_ptr, Qlane, Qbase, o);
                 a = e;
             }
             __syncwarp();                          // every lane is done with this tile
@@ -687,21 +691,21 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
     }
 }
 
-template <int KC, int KG, int DEG, int MV>
-int launch_fill_t(const FillParams &p, cudaStream_t s) {
+template <int KC, int KG, int DEG, int MV, bool MASKED>
+int launch_fill_m(const FillParams &p, cudaStream_t s) {
     static int grid_cap = 0;
     const int smem = static_cast<int>(sizeof(FillSmem<KC, KG, DEG, MV>)) * WSTR_WARPS_PER_CTA;
     if (grid_cap == 0) {
-        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
+        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV, MASKED>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // (shared memory must not be what limits the resident warps: take the largest carve-out)
-        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV>,
+        WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV, MASKED>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
         int dev = 0, sms = 0, per_sm = 0;
         WSTR_CUDA(cudaGetDevice(&dev));
         WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        WSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_fill_kernel<KC, KG, DEG, MV>,
+        WSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_fill_kernel<KC, KG, DEG, MV, MASKED>,
                                                                 32 * WSTR_WARPS_PER_CTA, smem));
         if (per_sm < 1) per_sm = 1;
         grid_cap = sms * per_sm;
@@ -709,9 +713,16 @@ int launch_fill_t(const FillParams &p, cudaStream_t s) {
     int grid = (p.n + WSTR_WARPS_PER_CTA - 1) / WSTR_WARPS_PER_CTA;
     if (grid > grid_cap) grid = grid_cap;
     if (grid < 1) return WSTR_OK;
-    dtw_fill_kernel<KC, KG, DEG, MV><<<grid, 32 * WSTR_WARPS_PER_CTA, smem, s>>>(p);
+    dtw_fill_kernel<KC, KG, DEG, MV, MASKED><<<grid, 32 * WSTR_WARPS_PER_CTA, smem, s>>>(p);
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;
+}
+
+// first pass (no mask) and second pass (mask bits) are separate instantiations, see WSTR_FILL_BOUNDS
+template <int KC, int KG, int DEG, int MV>
+int launch_fill_t(const FillParams &p, cudaStream_t s) {
+    if (p.maskbits) return launch_fill_m<KC, KG, DEG, MV, true>(p, s);
+    return launch_fill_m<KC, KG, DEG, MV, false>(p, s);
 }
 
 template <int KC, int KG, int MV>
