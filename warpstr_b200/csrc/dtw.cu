@@ -738,22 +738,61 @@ int launch_fill_deg(int deg, const FillParams &p, cudaStream_t s) {
 
 }  // namespace
 
-// the (chain, generic) slot splits the library is built with; keep in sync with kSplits in api.cu
-int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+// The (chain, generic) slot splits the library is built with; keep in sync with kSplits in api.cu.
+// The instantiations take minutes to compile, so this file is compiled several times in parallel, each
+// time with -DWSTR_FILL_PART=n for one group of them (__graft_entry__.py: FILL_PARTS); without the macro
+// everything lands in one object.
+#ifdef WSTR_FILL_PART
+#define WSTR_HAS_PART(n) (WSTR_FILL_PART == (n))
+#else
+#define WSTR_HAS_PART(n) 1
+#endif
 #define WSTR_CASE(KC_, KG_, MV_) \
     if (kc == KC_ && kg == KG_ && mv == MV_) return launch_fill_deg<KC_, KG_, MV_>(deg, p, s);
+
+int wstr_launch_fill_p0(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+int wstr_launch_fill_p1(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+int wstr_launch_fill_p2(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+int wstr_launch_fill_p3(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+
+#if WSTR_HAS_PART(0)
+int wstr_launch_fill_p0(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
     WSTR_CASE(7, 1, 4)
-    WSTR_CASE(6, 2, 4)
     WSTR_CASE(8, 1, 4)
     WSTR_CASE(6, 2, 2)
     WSTR_CASE(6, 2, 3)
+    return WSTR_ERR_UNSUPPORTED;
+}
+
+int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    int rc = wstr_launch_fill_p0(kc, kg, deg, mv, p, s);
+    if (rc == WSTR_ERR_UNSUPPORTED) rc = wstr_launch_fill_p1(kc, kg, deg, mv, p, s);
+    if (rc == WSTR_ERR_UNSUPPORTED) rc = wstr_launch_fill_p2(kc, kg, deg, mv, p, s);
+    if (rc == WSTR_ERR_UNSUPPORTED) rc = wstr_launch_fill_p3(kc, kg, deg, mv, p, s);
+    return rc;
+}
+#endif
+#if WSTR_HAS_PART(1)
+int wstr_launch_fill_p1(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(6, 2, 4)
     WSTR_CASE(6, 2, 5)
     WSTR_CASE(6, 2, 6)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+#if WSTR_HAS_PART(2)
+int wstr_launch_fill_p2(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
     WSTR_CASE(4, 4, 4)
     WSTR_CASE(8, 2, 4)
     WSTR_CASE(6, 4, 4)
-    WSTR_CASE(8, 4, 4)
-    WSTR_CASE(12, 4, 4)
-#undef WSTR_CASE
     return WSTR_ERR_UNSUPPORTED;
 }
+#endif
+#if WSTR_HAS_PART(3)
+int wstr_launch_fill_p3(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(8, 4, 4)
+    WSTR_CASE(12, 4, 4)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+#undef WSTR_CASE
