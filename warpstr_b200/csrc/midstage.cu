@@ -103,10 +103,11 @@ __device__ double pairwise_sum(const F &f, int start0, int n0) {
 //     r1 = a - q1*d (exact);                          q  = RN(q1 + r1*y)
 // is the correctly rounded a/d (Markstein 1990: one such step on a faithful q with a correctly
 // rounded reciprocal rounds correctly; the first step makes q1 faithful), i.e. the very bits
-// `a / d` gives, in 5 instructions.  Used only where nothing can over- or underflow (|d| and |a|
-// within 2^+-100 and 2^+-400); every other operand takes the plain division.  The identity was
-// also checked on the host against a/d for 4e9 operand pairs, adversarial significands included
-// (divisor all-ones / power of two / 1.5): no mismatch.
+// `a / d` gives, in 5 instructions.  Used only where nothing can over- or underflow: |d| within
+// 2^+-60 and the numerator zero or within 2^+-600, established per call (GUARD), per sample or per
+// read (`tame`); every other operand takes the plain division.  The identity is also checked on
+// the host against a/d (oracle/div_identity.c: 4e9 operand pairs over those ranges, adversarial
+// significands included -- divisor all ones / a power of two / 1.5 -- no mismatch).
 struct Divisor {
     double d, y;
     bool fast;     // 2^-60 <= |d| <= 2^60
