@@ -26,8 +26,8 @@ extern "C" {
 #define WSTR_OK 0
 #define WSTR_ERR_INVALID_ARGUMENT (-1)
 #define WSTR_ERR_CUDA (-2)
-#define WSTR_ERR_TOO_MANY_STATES (-3)     /* automaton larger than the widest kernel (512 states) */
-#define WSTR_ERR_UNSUPPORTED (-4)         /* e.g. min_values_per_state outside 2..8 */
+#define WSTR_ERR_TOO_MANY_STATES (-3)     /* states x min_values_per_state beyond the catch-all kernel's shared memory (~20 000) */
+#define WSTR_ERR_UNSUPPORTED (-4)         /* e.g. a state with more than 254 incoming edges */
 #define WSTR_ERR_WORKSPACE_TOO_SMALL (-5)
 #define WSTR_ERR_NO_DEVICE (-6)
 
@@ -79,18 +79,26 @@ int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off, const int
  *   in_ptr[S+1], in_idx[E]              CSR of State.incoming, order preserved
  *   rep_mask[S] StateAutomata.mask      last_base[S] last character of State.kmer
  *   endstate    StateAutomata.endstate  flank_length Locus.flank_length
- *   min_values_per_state                tr_calling_config.min_values_per_state (2..8)
+ *   min_values_per_state                tr_calling_config.min_values_per_state: any value > 1, as in
+ *                                       the reference (src/config.py:115).  Automata and settings the
+ *                                       register-resident kernels are built for (up to 512 states, in-degree
+ *                                       <= 4, min_values_per_state 2..6) run on those; everything else on the
+ *                                       catch-all kernel, same results.
  */
 int wstr_automaton_create(const double *values, const int32_t *seq_idx, const int32_t *in_ptr,
                           const int32_t *in_idx, const uint8_t *rep_mask, const uint8_t *last_base,
                           int32_t n_states, int32_t endstate, int32_t flank_length,
                           int32_t min_values_per_state, wstr_automaton **out);
 int wstr_automaton_destroy(wstr_automaton *a);
+/* Testing aid: when on, automata created afterwards use the catch-all kernel even where a
+ * specialised layout exists (the two must agree bit for bit). */
+int wstr_set_generic_only(int32_t on);
 /* Host-only dry run of the kernel layout (no device needed): info[0]=chain slots per lane (KC),
  * info[1]=generic slots per lane (KG), info[2]=candidates the generic slots are unrolled for (2 or 4;
  * 100+d: one for every generic slot but the last, d for the last),
  * info[3]=lanes holding chains, info[4]=states placed in generic slots; state_of_pos (optional)
- * receives the state at each of the 32*(KC+KG) positions, -1 = padding. */
+ * receives the state at each of the 32*(KC+KG) positions, -1 = padding.  All zero: no specialised
+ * layout, the automaton runs on the catch-all kernel. */
 int wstr_automaton_plan(const int32_t *in_ptr, const int32_t *in_idx, int32_t n_states,
                         int32_t min_values_per_state, int32_t *info, int32_t *state_of_pos, int32_t n_pos);
 /* info[0]=states per lane (K), info[1]=direction-code bits per lane per row (32/info[1] rows

@@ -32,7 +32,7 @@ def test_python_binding_covers_the_header(built_lib):
     from warpstr_b200 import _lib
     assert sorted(_lib.exported_symbols()) == _declared()
     assert _lib.lib().wstr_version() >= 100
-    assert _lib.lib().wstr_error_string(-3).decode().startswith('automaton has more states')
+    assert _lib.lib().wstr_error_string(-3).decode().startswith('automaton too large')
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
@@ -57,4 +57,7 @@ def test_host_only_entry_points_validate_arguments(built_lib):
     from warpstr_b200 import _lib
     import numpy as np
     with pytest.raises(_lib.WarpstrError):
-        _lib.automaton_plan(np.array([0, 0, 1], dtype=np.int32), np.array([0], dtype=np.int32), 2, 99)
+        _lib.automaton_plan(np.array([0, 0, 1], dtype=np.int32), np.array([0], dtype=np.int32), 2, 1)   # config.py:115
+    # nothing the reference accepts is refused: an unusual dwell goes to the catch-all kernel (all-zero plan)
+    info, sop = _lib.automaton_plan(np.array([0, 0, 1], dtype=np.int32), np.array([0], dtype=np.int32), 2, 99)
+    assert info['chain_slots'] == 0 and info['generic_slots'] == 0 and len(sop) == 0

@@ -25,9 +25,12 @@ def _run(cc, rc, name='HD', n=6, seed=70, noise=0.2, flank=110, engine=None):
     return res, want
 
 
-@pytest.mark.parametrize('mv', [2, 3, 4, 5, 6])
-def test_min_values_per_state(built_lib, oracle_c, mv):
-    res, want = _run(CallerConfig(min_values_per_state=mv), RescalerConfig())
+@pytest.mark.parametrize('mv', [2, 3, 4, 5, 6, 7, 8, 10])
+@pytest.mark.parametrize('name', ['HD', 'DM2', 'CAN', 'RFC1'])
+def test_min_values_per_state(built_lib, oracle_c, name, mv):
+    """Any dwell > 1 on any automaton, as the reference accepts (config.py:115, caller.py:206-218,
+    265-268): the whole two-pass call, bit-exact."""
+    res, want = _run(CallerConfig(min_values_per_state=mv), RescalerConfig(), name=name, n=4)
     for g, w in zip(res, want):
         assert g.seq == w.seq and g.resc_seq == w.resc_seq
         assert g.cost == w.cost and g.resc_cost == w.resc_cost
@@ -74,10 +77,12 @@ def test_host_engine_variants(built_lib, oracle_c, rc, engine):
         assert g.resc_cost == pytest.approx(w.resc_cost, rel=1e-9)
 
 
-def test_unsupported_mv_is_reported(built_lib):
+def test_invalid_mv_is_reported(built_lib):
+    """The reference asserts min_values_per_state > 1 (config.py:115)."""
     from warpstr_b200 import _lib
     from warpstr_b200.caller import CallerEngine
-    eng = CallerEngine(CallerConfig(min_values_per_state=7))
+    eng = CallerEngine(CallerConfig(min_values_per_state=4))
+    eng.cc.min_values_per_state = 1
     locus = synth.make_locus('AAAT', seed=1)
     with pytest.raises(_lib.WarpstrError):
         eng.add_automaton(StateAutomata(locus.template_regex), 110)

@@ -128,15 +128,31 @@ def test_kernel_layout_plan_invariants(built_lib):
                         assert pp % K >= KC or pp % K == KC - 1
 
 
-def test_layout_plan_rejects_what_the_kernels_cannot_hold(built_lib):
+def test_layout_plan_never_refuses_what_the_reference_accepts(built_lib):
+    """An automaton or dwell setting without a specialised layout plans onto the catch-all kernel
+    (all-zero plan), it is not an error; only what no kernel can hold is."""
     from warpstr_b200 import _lib
-    S = 600
+    S = 600                                              # more than the 512 register-resident positions
     ptr = np.arange(S + 1, dtype=np.int32)
     ptr[1:] -= 1
     ptr[0] = 0
     idx = np.arange(S - 1, dtype=np.int32)
-    with pytest.raises(_lib.WarpstrError):
-        _lib.automaton_plan(ptr, idx, S)
+    info, sop = _lib.automaton_plan(ptr, idx, S)
+    assert info['chain_slots'] == 0 and info['generic_slots'] == 0 and len(sop) == 0
+    with pytest.raises(_lib.WarpstrError):               # states x dwell beyond the shared memory of an SM
+        _lib.automaton_plan(ptr, idx, S, 64)
+    # every dwell setting on every locus shape of the test set plans: specialised kernels for 2..6
+    # (the 324-state reverse strand of (CAN) only at the default 4), the catch-all beyond
+    for name in ('HD', 'DM2', 'CAN', 'RFC1', 'FMR1_MGG'):
+        locus = synth.make_locus(name, seed=3)
+        for rx in (locus.template_regex, locus.reverse_regex):
+            sta = StateAutomata(rx)
+            for mv in (2, 3, 4, 5, 6, 7, 8, 12):
+                info, _ = _lib.automaton_plan(sta.in_ptr, sta.in_idx, sta.n_states, mv)
+                if mv > 6:
+                    assert info['chain_slots'] == 0
+                elif sta.n_states <= 320 or mv == 4:
+                    assert info['chain_slots'] > 0, (name, mv, info)
 
 
 def test_wrapper_unit_helpers():

@@ -51,6 +51,7 @@ _SIGNATURES = {
                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.POINTER(c_vp)]),
     'wstr_automaton_destroy': (ctypes.c_int, [c_vp]),
+    'wstr_set_generic_only': (ctypes.c_int, [ctypes.c_int32]),
     'wstr_automaton_plan': (ctypes.c_int, [c_i32p, c_i32p, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i32p,
                                            ctypes.c_int32]),
     'wstr_automaton_info': (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int32]),
@@ -185,6 +186,11 @@ def automaton_plan(in_ptr, in_idx, n_states: int, min_values_per_state: int = 4)
     keys = ('chain_slots', 'generic_slots', 'unrolled_in_degree', 'chain_lanes', 'generic_states')
     d = dict(zip(keys, (int(x) for x in info)))
     return d, sop[:32 * (d['chain_slots'] + d['generic_slots'])]
+
+
+def set_generic_only(on: bool) -> None:
+    """Testing aid: automata created while this is on use the catch-all kernel."""
+    check(lib().wstr_set_generic_only(1 if on else 0), 'wstr_set_generic_only')
 
 
 def _handles(automata: Sequence[DeviceAutomaton]):

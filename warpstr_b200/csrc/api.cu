@@ -28,7 +28,8 @@ extern "C" const char *wstr_error_string(int code) {
         case WSTR_OK: return "ok";
         case WSTR_ERR_INVALID_ARGUMENT: return "invalid argument";
         case WSTR_ERR_CUDA: return "CUDA error (see wstr_last_cuda_error)";
-        case WSTR_ERR_TOO_MANY_STATES: return "automaton has more states than the widest kernel supports (512)";
+        case WSTR_ERR_TOO_MANY_STATES:
+            return "automaton too large: states x min_values_per_state exceeds the catch-all kernel's shared memory";
         case WSTR_ERR_UNSUPPORTED: return "unsupported configuration";
         case WSTR_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
         case WSTR_ERR_NO_DEVICE: return "no CUDA device";
@@ -105,13 +106,15 @@ extern "C" int wstr_profile_read(double *ms, int32_t *launches, int32_t n) {
 // ------------------------------------------------------------------------------------------
 namespace {
 
+bool g_generic_only = false;   // wstr_set_generic_only: build automata for the catch-all kernel only
+
 struct Split {
     int kc, kg;
     unsigned mv_mask;   // bit mv set = instantiated for that min_values_per_state
 };
 // keep in sync with wstr_launch_fill in dtw.cu
 const Split kSplits[] = {{7, 1, 0x10}, {6, 2, 0x7c}, {8, 1, 0x10}, {4, 4, 0x10}, {8, 2, 0x10},
-                         {6, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
+                         {6, 4, 0x7c}, {8, 4, 0x10}, {12, 4, 0x10}};
 
 struct Layout {
     int KC = 0, KG = 0, DEG = 2, n_lanes = 0, n_generic = 0;
@@ -276,18 +279,30 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
                                      int32_t S, int32_t endstate, int32_t flank_length, int32_t mv,
                                      wstr_automaton **out) {
     if (!values || !seq_idx || !in_ptr || !out || S <= 0) return WSTR_ERR_INVALID_ARGUMENT;
-    if (mv < 2 || mv > WSTR_MAX_MV) return WSTR_ERR_UNSUPPORTED;
+    if (mv < 2) return WSTR_ERR_INVALID_ARGUMENT;           // reference: assert min_values_per_state > 1, config.py:115
     if (S <= mv) return WSTR_ERR_INVALID_ARGUMENT;          // reference: IndexError at caller.py:208
     if (endstate < 0 || endstate >= S) return WSTR_ERR_INVALID_ARGUMENT;
-    if (S > 32 * WSTR_MAX_K) return WSTR_ERR_TOO_MANY_STATES;
+    if (S > 32767) return WSTR_ERR_TOO_MANY_STATES;         // traceback tables hold state indices in 15 bits
     const int E = in_ptr[S];
     if (E > 0 && !in_idx) return WSTR_ERR_INVALID_ARGUMENT;
     for (int e = 0; e < E; ++e)
         if (in_idx[e] < 0 || in_idx[e] >= S) return WSTR_ERR_INVALID_ARGUMENT;
 
+    // the specialised register layout if there is one for this automaton and setting, else the
+    // catch-all kernel (dtw_any.cu): nothing the reference accepts is refused
     Layout L;
-    const int lrc = build_layout(S, in_ptr, in_idx, mv, L);
-    if (lrc != WSTR_OK) return lrc;
+    const bool any = g_generic_only || mv > WSTR_MAX_MV || build_layout(S, in_ptr, in_idx, mv, L) != WSTR_OK;
+    const int spad = (S + 31) / 32 * 32;
+    if (any) {
+        for (int j = 0; j < S; ++j)
+            if (in_ptr[j + 1] - in_ptr[j] > 254) return WSTR_ERR_UNSUPPORTED;      // one byte per direction code
+        if (wstr_any_smem_bytes(mv, spad) > WSTR_ANY_SMEM_MAX) return WSTR_ERR_TOO_MANY_STATES;
+        L.KC = L.KG = 0;
+        L.DEG = 0;
+        L.n_lanes = L.n_generic = 0;
+        L.state_of_pos.clear();
+        L.pos_of_state.assign(S, 0);
+    }
     const int KC = L.KC, KG = L.KG, K = KC + KG, NP = 32 * K;
     const int inf_cell = KG * 32 + 32;
 
@@ -362,7 +377,8 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     };
     const size_t o_v = take(sizeof(double) * NP), o_sop = take(sizeof(int16_t) * NP),
                  o_lt = take(sizeof(uint32_t) * lane_tab.size()), o_pt = take(sizeof(int32_t) * pred_tab.size()),
-                 o_val = take(sizeof(double) * S), o_sq = take(sizeof(int32_t) * S), o_rm = take(S), o_lb = take(S);
+                 o_val = take(sizeof(double) * S), o_sq = take(sizeof(int32_t) * S), o_rm = take(S), o_lb = take(S),
+                 o_ip = take(sizeof(int32_t) * (S + 1)), o_ii = take(sizeof(int32_t) * (size_t)std::max(E, 1));
     std::vector<unsigned char> blob(off, 0);
     memcpy(blob.data() + o_v, v_pos.data(), sizeof(double) * NP);
     memcpy(blob.data() + o_sop, sop.data(), sizeof(int16_t) * NP);
@@ -372,6 +388,8 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     memcpy(blob.data() + o_sq, seq_idx, sizeof(int32_t) * S);
     if (rep_mask) memcpy(blob.data() + o_rm, rep_mask, S);
     if (last_base) memcpy(blob.data() + o_lb, last_base, S);
+    memcpy(blob.data() + o_ip, in_ptr, sizeof(int32_t) * (S + 1));
+    if (E > 0) memcpy(blob.data() + o_ii, in_idx, sizeof(int32_t) * (size_t)E);
 
     void *d_blob = nullptr;
     WSTR_CUDA(cudaMalloc(&d_blob, off));
@@ -389,13 +407,24 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     d.KC = KC;
     d.KG = KG;
     d.DEG = L.DEG;
-    {                                // direction bits per lane and row (dtw.cu: DirFmt)
+    if (any) {                       // catch-all: one byte per cell, four rows per word (dtw_any.cu)
+        d.NB = 8;
+        d.RPW = 4;
+    } else {                         // direction bits per lane and row (dtw.cu: DirFmt)
         const int dmax = L.DEG >= 100 ? L.DEG - 100 : L.DEG;
         d.NB = L.DEG >= 100 ? KC + (KG - 1) + dmax : KC + KG * dmax;
+        d.RPW = 32 / d.NB;
     }
-    d.RPW = 32 / d.NB;
     d.S = S;
     d.end_pos = L.pos_of_state[endstate];
+    d.values = reinterpret_cast<const double *>(base + o_val);
+    d.seq_idx = reinterpret_cast<const int32_t *>(base + o_sq);
+    d.in_ptr = reinterpret_cast<const int32_t *>(base + o_ip);
+    d.in_idx = reinterpret_cast<const int32_t *>(base + o_ii);
+    d.any = any ? 1 : 0;
+    d.endstate = endstate;
+    d.after = after;
+    d.spad = spad;
     d.mv = mv;
     d.th1 = 6 * boundary;
     d.band6 = 6 * boundary;
@@ -409,7 +438,7 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
         for (int e = in_ptr[j]; e < in_ptr[j + 1]; ++e)
             if (seq_idx[in_idx[e]] >= after) d.band_closed = 0;
     }
-    for (int c = 0; c <= mv; ++c) d.init_pos[c] = L.pos_of_state[c];
+    for (int c = 0; c <= mv && c <= WSTR_MAX_MV; ++c) d.init_pos[c] = L.pos_of_state[c];
 
     wstr_automaton *a = new wstr_automaton();
     a->dev = d;
@@ -428,14 +457,23 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
     return WSTR_OK;
 }
 
+extern "C" int wstr_set_generic_only(int32_t on) {
+    g_generic_only = on != 0;
+    return WSTR_OK;
+}
+
 extern "C" int wstr_automaton_plan(const int32_t *in_ptr, const int32_t *in_idx, int32_t S, int32_t mv,
                                    int32_t *info, int32_t *state_of_pos, int32_t n_pos) {
-    if (!in_ptr || !info || S <= 0) return WSTR_ERR_INVALID_ARGUMENT;
-    if (mv < 2 || mv > WSTR_MAX_MV) return WSTR_ERR_UNSUPPORTED;
-    if (S > 32 * WSTR_MAX_K) return WSTR_ERR_TOO_MANY_STATES;
+    if (!in_ptr || !info || S <= 0 || mv < 2) return WSTR_ERR_INVALID_ARGUMENT;
     Layout L;
-    const int rc = build_layout(S, in_ptr, in_idx, mv, L);
-    if (rc != WSTR_OK) return rc;
+    if (g_generic_only || mv > WSTR_MAX_MV || build_layout(S, in_ptr, in_idx, mv, L) != WSTR_OK) {
+        // no specialised layout: the catch-all kernel takes it (dtw_any.cu)
+        for (int j = 0; j < S; ++j)
+            if (in_ptr[j + 1] - in_ptr[j] > 254) return WSTR_ERR_UNSUPPORTED;
+        if (wstr_any_smem_bytes(mv, (S + 31) / 32 * 32) > WSTR_ANY_SMEM_MAX) return WSTR_ERR_TOO_MANY_STATES;
+        for (int i = 0; i < 5; ++i) info[i] = 0;
+        return WSTR_OK;
+    }
     info[0] = L.KC;
     info[1] = L.KG;
     info[2] = L.DEG;
@@ -543,11 +581,13 @@ int stage_upload(StageSlot *sl, void *d_dst, size_t bytes, cudaStream_t s) {
 }
 
 inline int64_t dir_words(const wstr_automaton *a, int T) {   // RPW rows share a word per lane (dtw.cu: DirFmt)
+    if (a->dev.any) return ((int64_t)T + 3) / 4 * a->dev.spad;   // ... per state in the catch-all (dtw_any.cu)
     return ((int64_t)T + a->dev.RPW - 1) / a->dev.RPW * 32;
 }
 
 struct FillLaunch {
-    int kc, kg, deg;
+    int kc, kg, deg;   // 0, 0, 0: the catch-all kernel
+    int spad_max;      // catch-all: widest automaton of the launch
     int begin, n;      // slice of the order array
     int counter;       // index of its work counter
 };
@@ -627,12 +667,14 @@ int plan_fill(wstr_automaton *const *automata, int n_automata, const int32_t *re
             fl.kc = ref.KC;
             fl.kg = ref.KG;
             fl.deg = ref.DEG;
+            fl.spad_max = 0;
             fl.begin = filled;
             for (int i = i0; i < nw; ++i) {
                 const DevAutomaton &o = automata[meta[wave_begin + i].aut]->dev;
                 if (!done[i] && o.KC == ref.KC && o.KG == ref.KG && o.DEG == ref.DEG) {
                     order[filled++] = wave_begin + i;
                     done[i] = 1;
+                    fl.spad_max = std::max(fl.spad_max, (int)o.spad);
                 }
             }
             fl.n = filled - fl.begin;
@@ -674,7 +716,8 @@ int run_fill(const std::vector<Wave> &waves, const FillDevice &fd, int mv, const
             fp.status = d_status;
             fp.respect_status = respect_status;
             wstr_prof_begin(0, s);
-            const int rc = wstr_launch_fill(fl.kc, fl.kg, fl.deg, mv, fp, s);
+            const int rc = fl.kc + fl.kg == 0 ? wstr_launch_fill_any(mv, fl.spad_max, fp, s)
+                                              : wstr_launch_fill(fl.kc, fl.kg, fl.deg, mv, fp, s);
             wstr_prof_end(s);
             if (rc != WSTR_OK) return rc;
         }

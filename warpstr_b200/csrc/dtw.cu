@@ -750,10 +750,14 @@ int launch_fill_deg(int deg, const FillParams &p, cudaStream_t s) {
 #define WSTR_CASE(KC_, KG_, MV_) \
     if (kc == KC_ && kg == KG_ && mv == MV_) return launch_fill_deg<KC_, KG_, MV_>(deg, p, s);
 
-int wstr_launch_fill_p0(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
-int wstr_launch_fill_p1(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
-int wstr_launch_fill_p2(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
-int wstr_launch_fill_p3(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+#define WSTR_DECL_PART(n) int wstr_launch_fill_p##n(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+WSTR_DECL_PART(0)
+WSTR_DECL_PART(1)
+WSTR_DECL_PART(2)
+WSTR_DECL_PART(3)
+WSTR_DECL_PART(4)
+WSTR_DECL_PART(5)
+#undef WSTR_DECL_PART
 
 #if WSTR_HAS_PART(0)
 int wstr_launch_fill_p0(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
@@ -765,11 +769,14 @@ int wstr_launch_fill_p0(int kc, int kg, int deg, int mv, const FillParams &p, cu
 }
 
 int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
-    int rc = wstr_launch_fill_p0(kc, kg, deg, mv, p, s);
-    if (rc == WSTR_ERR_UNSUPPORTED) rc = wstr_launch_fill_p1(kc, kg, deg, mv, p, s);
-    if (rc == WSTR_ERR_UNSUPPORTED) rc = wstr_launch_fill_p2(kc, kg, deg, mv, p, s);
-    if (rc == WSTR_ERR_UNSUPPORTED) rc = wstr_launch_fill_p3(kc, kg, deg, mv, p, s);
-    return rc;
+    typedef int (*part_fn)(int, int, int, int, const FillParams &, cudaStream_t);
+    static const part_fn parts[] = {wstr_launch_fill_p0, wstr_launch_fill_p1, wstr_launch_fill_p2,
+                                    wstr_launch_fill_p3, wstr_launch_fill_p4, wstr_launch_fill_p5};
+    for (part_fn f : parts) {
+        const int rc = f(kc, kg, deg, mv, p, s);
+        if (rc != WSTR_ERR_UNSUPPORTED) return rc;
+    }
+    return WSTR_ERR_UNSUPPORTED;
 }
 #endif
 #if WSTR_HAS_PART(1)
@@ -792,6 +799,21 @@ int wstr_launch_fill_p2(int kc, int kg, int deg, int mv, const FillParams &p, cu
 int wstr_launch_fill_p3(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
     WSTR_CASE(8, 4, 4)
     WSTR_CASE(12, 4, 4)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+// (6,4) holds every automaton of up to ~320 states: the specialised kernel of the other dwell settings
+#if WSTR_HAS_PART(4)
+int wstr_launch_fill_p4(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(6, 4, 2)
+    WSTR_CASE(6, 4, 3)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+#if WSTR_HAS_PART(5)
+int wstr_launch_fill_p5(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(6, 4, 5)
+    WSTR_CASE(6, 4, 6)
     return WSTR_ERR_UNSUPPORTED;
 }
 #endif

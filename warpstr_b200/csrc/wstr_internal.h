@@ -6,7 +6,10 @@
 #include "warpstr_b200.h"
 
 #define WSTR_MAX_K 16            // states per lane in the widest kernel (32*16 = 512 positions)
-#define WSTR_MAX_MV 8
+#define WSTR_MAX_MV 8            // largest min_values_per_state of the specialised kernels (the catch-all has no limit)
+#define WSTR_ANY_THREADS 128     // CTA of the catch-all kernel
+#define WSTR_ANY_TILE 128        // samples per signal tile of the catch-all kernel
+#define WSTR_ANY_SMEM_MAX (200 * 1024)
 #define WSTR_SIG_CHUNK 126       // samples per bulk-copied signal tile (1008 B; a multiple of the 3-row cycle)
 // warps per CTA of the fill kernel.  Warps never talk to each other, so a CTA is one warp: every
 // shared-memory address is then a compile-time constant (the 3-row cycle of the (7,1) kernel is
@@ -37,6 +40,16 @@ struct DevAutomaton {
     int32_t band6;                   // 6*(flank_length-10) (second threshold = T - band6)
     int32_t band_closed;             // no edge leads from outside the end band's skipped set into it
     int32_t init_pos[WSTR_MAX_MV + 1];  // positions of states 0..mv (row-0 initialisation)
+    // ---- catch-all kernel (dtw_any.cu): the automaton as the reference holds it -------------------
+    // any != 0: no specialised layout (K = 0); the tables below are valid for every automaton
+    const double *values;            // [S]
+    const int32_t *seq_idx;          // [S]
+    const int32_t *in_ptr;           // [S+1]
+    const int32_t *in_idx;           // [E] incoming states, list order
+    int32_t any;
+    int32_t endstate;
+    int32_t after;                   // end band skips states with seq_idx < after (caller.py:211-212)
+    int32_t spad;                    // S rounded up to 32: row stride of the catch-all direction words
 };
 
 // Per-read record of one wave.
@@ -138,3 +151,6 @@ void wstr_prof_end(cudaStream_t s);
 
 // kernels / launchers (dtw.cu)
 int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s);
+// catch-all (dtw_any.cu): any min_values_per_state, any in-degree; spad_max = widest automaton of the launch
+int wstr_launch_fill_any(int mv, int spad_max, const FillParams &p, cudaStream_t s);
+size_t wstr_any_smem_bytes(int mv, int spad_max);
