@@ -51,42 +51,77 @@ def parse():
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU side: the oracle's port of the reference caller (bench.py may execute oracle/ only here)
+# CPU side (bench.py may execute oracle/ only here)
+#   kind "reference": the unmodified reference's warpstr_call_sequential (src/caller/wrapper.py:292-331),
+#       byte-compiled into oracle/_ref by oracle/build_ref.py, reads spread over a process pool exactly like
+#       CallerWrapper.run (wrapper.py:107-109) -- what `--impl reference` times;
+#   kind "port": the oracle's cell-by-cell Python port of the same DP + numpy/scipy mid-stage (4-9x faster than
+#       the reference) -- the cpu_baseline of our own arm, and the fallback when oracle/_ref was not built.
 # ---------------------------------------------------------------------------------------------------
 _CPU_CTX = {}
 
 
-def _cpu_init(locus_name, seed):
-    from oracle import caller_oracle as co
+def _cpu_init(locus_name, seed, kind):
     from warpstr_b200 import synth
-    from warpstr_b200.automata import StateAutomata
     locus = synth.make_locus(locus_name, seed=seed)
+    _CPU_CTX['kind'] = kind
+    _CPU_CTX['F'] = locus.flank_length
+    if kind == 'reference':
+        from oracle import refshim
+        ref = refshim.load()
+        _CPU_CTX['ref'] = ref
+        _CPU_CTX['sta'] = [ref.StateAutomata(locus.template_regex), ref.StateAutomata(locus.reverse_regex)]
+        return
+    from oracle import caller_oracle as co
+    from warpstr_b200.automata import StateAutomata
     _CPU_CTX['tb'] = [co.tables_from(StateAutomata(locus.template_regex)),
                       co.tables_from(StateAutomata(locus.reverse_regex))]
     _CPU_CTX['co'] = co
-    _CPU_CTX['F'] = locus.flank_length
 
 
 def _cpu_one(job):
     sig, rev = job
+    if _CPU_CTX['kind'] == 'reference':
+        ref = _CPU_CTX['ref']
+        rs = ref.wrapper.ReadSignal(name='bench', reverse=bool(rev), signal=sig)
+        r = ref.wrapper.warpstr_call_sequential(rs, _CPU_CTX['F'], _CPU_CTX['sta'][int(rev)], None)
+        return len(r.resc_seq)
     co = _CPU_CTX['co']
     r = co.run_read(sig, _CPU_CTX['tb'][int(rev)], _CPU_CTX['F'], bool(rev), impl='scalar')
     return len(r.resc_seq)
 
 
-def cpu_reference_run(locus_name, seed, signals, revs, cores):
-    """Port of the reference's Python DP (cell-by-cell loops, float64) + its numpy/scipy
-    mid-stage, reads spread over a process pool exactly like CallerWrapper.run
-    (src/caller/wrapper.py:107-109).  Returns (seconds, lengths)."""
-    import multiprocessing as mp
-    jobs = list(zip(signals, revs))
-    ctx = mp.get_context('fork')
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(locus_name, seed)) as pool:
-        pool.map(_cpu_one, jobs[:cores])            # warm the workers (imports, tables)
+class CpuPool:
+    """A process pool over reads, as CallerWrapper.run uses (src/caller/wrapper.py:107-109)."""
+
+    def __init__(self, locus_name, seed, cores, kind):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init, initargs=(locus_name, seed, kind))
+
+    def run(self, signals, revs):
+        """(seconds, allele lengths) of one pass over the sample."""
+        jobs = list(zip(signals, revs))
         t0 = time.perf_counter()
-        out = pool.map(_cpu_one, jobs)
-        dt = time.perf_counter() - t0
-    return dt, out
+        out = self.pool.map(_cpu_one, jobs, chunksize=1)
+        return time.perf_counter() - t0, out
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_kind():
+    from oracle import refshim
+    return 'reference' if refshim.compiled_available() or refshim.source_available() else 'port'
+
+
+CPU_SAMPLE_NOTE = {
+    'reference': 'the unmodified reference (src/caller/wrapper.py warpstr_call_sequential, byte-compiled to oracle/_ref), '
+                 'Pool over reads as CallerWrapper.run does',
+    'port': "the oracle's pure-Python float64 port of caller.py:198-301 + numpy/scipy mid-stage (4-9x faster per read "
+            'than the unmodified reference), Pool over reads',
+}
 
 
 def host_cores():
@@ -162,24 +197,26 @@ def main():
         if rank != 0:
             return
         from warpstr_b200 import synth
-        n = args.cpu_reads or cores
+        kind = cpu_kind()
+        n = args.cpu_reads or cores                      # one read per core and step: 5-10 s of the reference per step
         locus = synth.make_locus(args.locus, seed=1)
         reads = synth.make_reads(locus, n, seed=1000 * CONFIG_ID)
         sigs, revs = [r.signal for r in reads], [r.reverse for r in reads]
+        pool = CpuPool(args.locus, 1, cores, kind)
         for _ in range(args.warmup):
-            cpu_reference_run(args.locus, 1, sigs[:cores], revs[:cores], cores)
+            pool.run(sigs, revs)
         total = 0.0
         for _ in range(args.steps):
-            dt, _ = cpu_reference_run(args.locus, 1, sigs, revs, cores)
+            dt, _ = pool.run(sigs, revs)
             total += dt
+        pool.close()
         value = n * args.steps / total
         line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                 'sample': f'{n} reads of the same workload per step, Pool({cores}) over reads; '
-                                           'pure-Python float64 DP port of caller.py:198-301 + numpy/scipy mid-stage'},
+                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                 'sample': f'{n} reads of the same workload per step; ' + CPU_SAMPLE_NOTE[kind]},
                 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
         return
@@ -201,13 +238,16 @@ def main():
         n_cpu = args.cpu_reads or 2 * cores
         locus0 = synth.make_locus(args.locus, seed=1)
         sample = synth.make_reads(locus0, n_cpu, seed=1000 * CONFIG_ID)
-        dt, cpu_len = cpu_reference_run(args.locus, 1, [r.signal for r in sample], [r.reverse for r in sample], cores)
-        cells = float(sum(2 * len(r.signal) for r in sample)) * 241
+        pool = CpuPool(args.locus, 1, cores, 'port')
+        pool.run([r.signal for r in sample[:cores]], [r.reverse for r in sample[:cores]])   # warm the workers
+        dt, cpu_len = pool.run([r.signal for r in sample], [r.reverse for r in sample])
+        pool.close()
+        s0 = [StateAutomata(locus0.template_regex).n_states, StateAutomata(locus0.reverse_regex).n_states]
+        cells = float(sum(2 * len(r.signal) * s0[int(r.reverse)] for r in sample))
         cpu_baseline = {'value': n_cpu / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'mcups': cells / dt / 1e6,
-                        'sample': f'{n_cpu} reads of the same workload, Pool({cores}) over reads; pure-Python float64 '
-                                  'DP port of caller.py:198-301 + numpy/scipy mid-stage (the unmodified reference '
-                                  'measured 4.5-10 s/read/core in the build container, this port ~1.1 s)'}
+                        'sample': f'{n_cpu} reads of the same workload; ' + CPU_SAMPLE_NOTE['port'] +
+                                  ' (`--impl reference` times the unmodified reference itself)'}
 
     locus = synth.make_locus(args.locus, seed=1)
     stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY.  Import the *unmodified* reference (fmfi-compbio/warpstr)
-from /root/reference inside this container so that its own functions can be used
-to pin the oracle and to generate golden vectors (tests/golden/, see
-oracle/make_golden.py).  /root/reference does not exist on the GPU box, so
-nothing that runs there may import this module.
+so that its own functions can be used to pin the oracle, to generate golden vectors
+(tests/golden/, see oracle/make_golden.py) and as the timed CPU arm of bench.py.
+In this container the modules come from /root/reference; on the GPU box, where that
+tree does not exist, from oracle/_ref/ -- the same modules byte-compiled by
+oracle/build_ref.py (source-less .pyc, git-ignored, shipped like a built .so).
 
 The reference parses argv and its YAML config at import time
 (src/config.py:174-210), needs h5py / pysam / Biopython / matplotlib / seaborn
@@ -17,11 +18,13 @@ import types
 import numpy as np
 
 REF_ROOT = '/root/reference'
+_HERE = os.path.dirname(os.path.abspath(__file__))
+COMPILED_ROOT = os.path.join(_HERE, '_ref')
 
 _CFG = """\
 reference_path: /nonexistent/GRCh38.fa
 output: {out}
-pore_model_path: {root}/example/deps/template_median68pA.model
+pore_model_path: {pore}
 single_read_extraction: False
 guppy_annotation: False
 exp_signal_generation: False
@@ -43,7 +46,16 @@ _loaded = None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, 'src', 'caller'))
+    return source_available() or compiled_available()
+
+
+def source_available() -> bool:
+    # WSTR_REF_COMPILED=1: use oracle/_ref even where the source tree exists (to test that path here)
+    return os.path.isdir(os.path.join(REF_ROOT, 'src', 'caller')) and not os.environ.get('WSTR_REF_COMPILED')
+
+
+def compiled_available() -> bool:
+    return os.path.exists(os.path.join(COMPILED_ROOT, 'src', 'caller', 'wrapper.pyc'))
 
 
 def _stub(name, **kw):
@@ -74,14 +86,27 @@ def load():
     if _loaded is not None:
         return _loaded
     if not available():
-        raise RuntimeError('reference tree not present at ' + REF_ROOT)
+        raise RuntimeError(f'reference neither at {REF_ROOT} nor compiled under {COMPILED_ROOT}')
     tmp = tempfile.mkdtemp(prefix='warpstr_oracle_')
     cfg = os.path.join(tmp, 'oracle_cfg.yaml')
-    with open(cfg, 'w') as fh:
-        fh.write(_CFG.format(out=tmp, root=REF_ROOT))
     old_cwd, old_argv = os.getcwd(), sys.argv
-    os.chdir(REF_ROOT)
-    sys.path.insert(0, REF_ROOT)
+    if source_available():
+        root, cwd = REF_ROOT, REF_ROOT
+        pore = os.path.join(REF_ROOT, 'example', 'deps', 'template_median68pA.model')
+    else:
+        # the compiled modules; src/config.py:13-26 reads <cwd>/src/default.yaml at import: write this
+        # repo's table of the same defaults there, and use the bundled copy of the k-mer table
+        import yaml
+        from warpstr_b200 import config as our_config
+        root, cwd = COMPILED_ROOT, tmp
+        os.makedirs(os.path.join(tmp, 'src'), exist_ok=True)
+        with open(os.path.join(tmp, 'src', 'default.yaml'), 'w') as fh:
+            yaml.safe_dump(our_config.DEFAULTS, fh)
+        pore = our_config.DEFAULT_PORE_MODEL
+    with open(cfg, 'w') as fh:
+        fh.write(_CFG.format(out=tmp, pore=pore))
+    os.chdir(cwd)
+    sys.path.insert(0, root)
     sys.argv = ['WarpSTR.py', cfg]
     try:
         if not hasattr(np, 'bool8'):
@@ -112,7 +137,7 @@ def load():
         os.chdir(old_cwd)
         sys.argv = old_argv
     ns = types.SimpleNamespace(
-        config=ref_config, caller=ref_caller, wrapper=ref_wrapper,
+        root=root, config=ref_config, caller=ref_caller, wrapper=ref_wrapper,
         StateAutomata=StateAutomata, WarpSTR=ref_caller.WarpSTR,
         Fast5=Fast5, normalize_signal_mad=normalize_signal_mad,
         pore_model=pore_model, Squiggler=Squiggler)

@@ -199,3 +199,19 @@ def test_exact_division_identity_the_midstage_relies_on(tmp_path):
     out = subprocess.run([exe, '5000000'], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert 'two_step_mismatches=0' in out.stdout
+
+
+def test_pore_model_path_of_a_config(tmp_path):
+    """The reference's default path resolves to the bundled table; a user's own path that does not
+    exist fails like the reference (pore_model.py:22-24) instead of silently using another model."""
+    from warpstr_b200 import config as cfg
+    base = {'loci': [{'name': 'x', 'sequence': '(AAAT)'}], 'output': str(tmp_path)}
+    c = cfg.config_from_dict(dict(base))
+    assert c.pore_model_path == cfg.DEFAULT_PORE_MODEL
+    c = cfg.config_from_dict(dict(base, pore_model_path='example/deps/template_median68pA.model'))
+    assert c.pore_model_path == cfg.DEFAULT_PORE_MODEL
+    with pytest.raises(FileNotFoundError):
+        cfg.config_from_dict(dict(base, pore_model_path=str(tmp_path / 'r10_custom.model')))
+    own = tmp_path / 'own.model'
+    own.write_text(open(cfg.DEFAULT_PORE_MODEL).read())
+    assert cfg.config_from_dict(dict(base, pore_model_path=str(own))).pore_model_path == str(own)

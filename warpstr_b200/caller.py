@@ -6,6 +6,7 @@ read_name).run(signal) / .warp(signal, mask)`` (:107-193).  The DP fill and trac
 both passes run in the CUDA kernels behind ``wstr_warp_batch``; :class:`CallerEngine`
 batches reads so that thousands of them are in flight at once.
 """
+import hashlib
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -98,6 +99,7 @@ class CallerEngine:
         self.tables: List[dict] = []
         self._ws = None
         self._ws_at_limit = False
+        self._ws_need_seen = 0
         self._lane_ws = {}
         self._lane_streams = None
         self._copy_stream = None
@@ -123,13 +125,21 @@ class CallerEngine:
     # -- device helpers ---------------------------------------------------------------------
     def _workspace(self, need: int, lane: int = 0):
         if lane:
-            # extra compute lanes of the pipelined call own a workspace each (sized for their chunks)
+            # extra compute lanes of the pipelined call own a workspace each (sized for their chunks), under
+            # the same limits as the first: the explicit one, else 60 % of what is free when it has to grow
             ws = self._lane_ws.get(lane)
             if ws is None or ws.numel() < need:
                 import torch
-                self._lane_ws[lane] = None
-                ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-                self._lane_ws[lane] = ws
+                have = ws.numel() if ws is not None else 0
+                limit = self.workspace_limit
+                if limit is None:
+                    free, _ = torch.cuda.mem_get_info(self.device)
+                    limit = int(free * 0.6) + have
+                size = min(need, max(limit, 1 << 20))
+                if size > have:
+                    self._lane_ws[lane] = None
+                    ws = torch.empty(size, dtype=torch.uint8, device=self.device)
+                    self._lane_ws[lane] = ws
             return ws
         return self._workspace0(need)
 
@@ -139,8 +149,9 @@ class CallerEngine:
         to (the call can block for tens of milliseconds while the GPU is busy)."""
         import torch
         ws = self._ws
-        if ws is not None and (ws.numel() >= need or self._ws_at_limit):
+        if ws is not None and (ws.numel() >= need or (self._ws_at_limit and need <= self._ws_need_seen)):
             return ws
+        self._ws_need_seen = need        # a larger request re-evaluates the limit (memory may have been freed)
         limit = self.workspace_limit
         if limit is None:
             free, _ = torch.cuda.mem_get_info(self.device)
@@ -265,7 +276,11 @@ class CallerEngine:
         sequence bytes.  The batch is cut into chunks of up to ``chunk_reads`` reads; one copy
         stream moves the chunks to the device, another brings results back, and the calls
         alternate between ``lanes`` compute streams so that one chunk's kernel tails and
-        mid-stage overlap the next chunk's DP.  ``call_batch`` wraps this into ``CallerResult`` objects."""
+        mid-stage overlap the next chunk's DP.  ``call_batch`` wraps this into ``CallerResult`` objects.
+
+        len/cost/status come back as fresh arrays (-1 / NaN where ``status`` is not 0 -- a read the
+        reference would have raised on, see ``_STATUS_ERRORS``); ``seq1``/``seq2`` are views of pinned
+        buffers the engine reuses, valid until the next ``call_arrays`` on it."""
         import torch
         n = len(lengths)
         lengths = np.asarray(lengths, dtype=np.int32)
@@ -365,7 +380,16 @@ class CallerEngine:
             cs_out.synchronize()
             comp.wait_stream(cs_in)
             comp.wait_stream(cs_out)
-        res = {k: out[k][:n].numpy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+        # per-read scalars are handed back as copies; reads the device could not finish (status != 0) carry
+        # -1 / NaN instead of whatever the buffers held.  The sequence bytes are views of the engine's pinned
+        # buffers (hundreds of MB per 100 000 reads): valid until the next call_arrays on this engine.
+        res = {k: out[k][:n].numpy().copy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+        bad = res['status'] != 0
+        if bad.any():
+            res['len1'][bad] = -1
+            res['len2'][bad] = -1
+            res['cost1'][bad] = np.nan
+            res['cost2'][bad] = np.nan
         if want_seq:
             res['seq1'] = out['seq1'][:int(seq_off[-1])].numpy()
             res['seq2'] = out['seq2'][:int(seq_off[-1])].numpy()
@@ -535,11 +559,19 @@ class WarpSTR:
 
     def __post_init__(self):
         self._engine = self.engine or default_engine()
-        key = (id(self.states), self.flank_length)
+        # the reference builds one WarpSTR per read from the locus's automaton (wrapper.py:289,329): the
+        # uploaded tables are shared between them, keyed on their content (ids of Python objects can be
+        # recycled once a locus's automaton has been collected)
+        view = _StatesView(self.states, self.endstate, self.repeat_mask)
+        key = hashlib.sha1(b''.join(a.tobytes() for a in (view.values, view.seq_idx, view.in_ptr, view.in_idx,
+                                                            view.rep_mask, view.last_base)) +
+                           repr((view.endstate, int(self.flank_length),
+                                 int(self._engine.cc.min_values_per_state))).encode()).hexdigest()
         cache = self._engine.__dict__.setdefault('_seam_cache', {})
         if key not in cache:
-            cache[key] = self._engine.add_automaton(_StatesView(self.states, self.endstate, self.repeat_mask),
-                                                    self.flank_length)
+            if len(cache) >= 64:                       # a long run over many loci: drop the oldest upload
+                cache.pop(next(iter(cache)))
+            cache[key] = self._engine.add_automaton(view, self.flank_length)
         self._aut = cache[key]
 
     def warp(self, signal: np.ndarray, mask: Optional[List[bool]] = None) -> WarpResult:

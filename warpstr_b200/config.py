@@ -154,10 +154,15 @@ def config_from_dict(raw: Dict[str, Any], base_dir: Optional[str] = None) -> Con
     if pore and not os.path.isabs(pore) and base_dir:
         cand = os.path.join(base_dir, pore)
         pore = cand if os.path.exists(cand) else pore
-    if not pore or not os.path.exists(pore):
-        # WarpSTR ships exactly one model (example/deps/template_median68pA.model);
-        # the same table is bundled with this package.
+    if not pore or (not os.path.exists(pore) and
+                    os.path.normpath(str(raw.get('pore_model_path'))) == os.path.normpath(DEFAULTS['pore_model_path'])):
+        # the reference's default (example/deps/template_median68pA.model, relative to its checkout):
+        # the same table is bundled with this package
         pore = DEFAULT_PORE_MODEL
+    elif not os.path.exists(pore):
+        # a user's own model that is not there: fail like the reference (pore_model.py:22-24), do not
+        # silently call with the levels of another chemistry
+        raise FileNotFoundError(f'Not found pore model table at path {pore}')
     loci = [LocusConfig(**{k: v for k, v in item.items()
                            if k in LocusConfig.__dataclass_fields__})
             for item in (raw.get('loci') or [])]
