@@ -47,6 +47,16 @@ def parse():
     ap.add_argument('--locus', default=LOCUS)
     ap.add_argument('--cpu-reads', type=int, default=0, help='reads of the CPU baseline sample (0 = 2 per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parity-reads', type=int, default=-1,
+                    help='reads of the batch checked against the oracle (-1: 10000 at N=1, 2000 at N>1)')
+    ap.add_argument('--legs', default='c3,panel',
+                    help='extra strong-scaling legs through the sharded call: c3 (FMR1, (MGG), DM2; 100k reads), '
+                         'panel (C5: 50 loci x 20k reads); empty = none')
+    ap.add_argument('--panel-loci', type=int, default=50)
+    ap.add_argument('--panel-reads', type=int, default=20000, help='reads per locus of the panel leg')
+    ap.add_argument('--c3-reads', type=int, default=33334, help='reads per locus of the c3 leg')
+    ap.add_argument('--leg-base', type=int, default=2000, help='noiseless base reads per locus of a leg')
+    ap.add_argument('--leg-steps', type=int, default=3)
     return ap.parse_args()
 
 
@@ -179,6 +189,116 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------
+# Strong-scaling legs (BASELINE configs[2] and [4]): a fixed multi-locus panel sharded over the ranks by DP
+# cells (LPT), every rank calls its shard, one id-keyed NCCL gather returns everybody's per-read results.
+# ---------------------------------------------------------------------------------------------------
+LEG_SPECS = {
+    'c3': dict(patterns=('FMR1', 'FMR1_MGG', 'DM2'), n_loci=3, seed=31,
+               what='C3: FMR1 ((CGG){AGG}), ambiguous-base (MGG) and DM2 (in-degree 4), BASELINE configs[2]'),
+    'panel': dict(patterns=None, n_loci=None, seed=51,
+                  what='C5: multi-locus panel, mixed patterns with random flanks, BASELINE configs[4]'),
+}
+
+
+def leg_prepare(name, args, workers):
+    """Host part of a leg, before CUDA exists in this process: loci and their noiseless base reads."""
+    from warpstr_b200 import synth
+    spec = LEG_SPECS[name]
+    n_loci = spec['n_loci'] or args.panel_loci
+    per = args.c3_reads if name == 'c3' else args.panel_reads
+    loci = synth.make_panel(n_loci, seed=spec['seed'], patterns=spec['patterns'] or synth.PANEL_MIX)
+    base = synth.make_panel_base(loci, min(args.leg_base, per), seed=spec['seed'], workers=workers)
+    return dict(name=name, loci=loci, base=base, per=per, seed=spec['seed'], what=spec['what'])
+
+
+def leg_run(leg, args, rank, world, barrier):
+    import torch
+    import torch.distributed as dist
+    from warpstr_b200 import shard, synth
+    from warpstr_b200.automata import StateAutomata
+    from warpstr_b200.caller import CallerEngine
+    loci, base, per = leg['loci'], leg['base'], leg['per']
+    n_total = len(loci) * per
+    regexes = []
+    for loc in loci:
+        regexes += [loc.template_regex, loc.reverse_regex]
+    stas = [StateAutomata(rx) for rx in regexes]
+    eng = CallerEngine()
+    ids = np.array([eng.add_automaton(s, 110) for s in stas], dtype=np.int32)
+    shapes = sorted({(i['chain_slots'], i['generic_slots']) for i in (a.info() for a in eng.automata)})
+    n_states = np.array([s.n_states for s in stas], dtype=np.int64)
+    locus_of, bidx, lengths_all, rev_all, truth_all = synth.panel_read_table(base, per)
+    aut_all = ids[2 * locus_of + rev_all]
+    shards = shard.partition_reads(lengths_all.astype(np.float64) * n_states[2 * locus_of + rev_all], world)
+    counts = [len(x) for x in shards]
+    mine = shards[rank]
+    dev = torch.device('cuda', torch.cuda.current_device())
+    d_sig, off, lengths = synth.materialize_panel_reads(base, per, mine, 0.15, leg['seed'], dev)
+    aut, rev = aut_all[mine], rev_all[mine]
+    d_ids = torch.as_tensor(mine, device=dev)
+    # oracle sample: reads spread over every locus (and so over every rank's shard), materialised here as well
+    n_sample = max(200, 4 * len(loci))
+    sample = np.unique(np.linspace(0, n_total - 1, n_sample).astype(np.int64))
+    want = None
+    if rank == 0:
+        from oracle import bulk
+        s_sig, s_off, s_len = synth.materialize_panel_reads(base, per, sample, 0.15, leg['seed'], dev)
+        s_host = s_sig.cpu().numpy()
+        want = bulk.run_reads(regexes, 110, [s_host[o:o + n] for o, n in zip(s_off, s_len)],
+                              (2 * locus_of + rev_all)[sample], rev_all[sample], workers=1)
+        del s_sig
+
+    def step():
+        return shard.call_sharded_packed(eng, mine, d_sig, off, lengths, aut, rev, counts, n_total, d_ids=d_ids)
+
+    for _ in range(max(3, args.warmup if args.warmup < 4 else 3)):
+        g = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.leg_steps):
+        g = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.leg_steps
+    len1, len2, status = g['len1'].cpu().numpy(), g['len2'].cpu().numpy(), g['status'].cpu().numpy()
+    cost2 = g['cost2'].cpu().numpy()
+    out = None
+    if rank == 0:
+        ok = status == 0
+        mism = 0
+        for i, w in zip(sample, want):
+            if w[0] == 'error':
+                mism += int(status[i] == 0)
+            else:
+                mism += int(status[i] != 0 or len1[i] != len(w[0]) or len2[i] != len(w[1]) or cost2[i] != w[3])
+        checksum = int((np.arange(1, n_total + 1, dtype=np.int64) * np.where(ok, len2, -1).astype(np.int64)).sum() % 2305843009213693951)
+        loads = np.array([float((lengths_all[x].astype(np.float64) * n_states[(2 * locus_of + rev_all)[x]]).sum())
+                          for x in shards])
+        out = {'workload': leg['what'], 'loci': len(loci), 'automata_resident': len(stas), 'kernel_shapes': shapes,
+               'reads': n_total, 'reads_per_locus': per,
+               'distinct_base_reads_per_locus': int(len(base[0][2])),
+               'scaling': 'strong', 'value': n_total / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+               'steps': args.leg_steps,
+               'path': 'shard.partition_reads (LPT by T*S) -> CallerEngine.call_packed per rank -> shard.gather_by_id '
+                       '(id-keyed NCCL all_gather, 32 B/read)',
+               'shard_reads': counts, 'shard_load_imbalance': float(loads.max() / loads.mean()),
+               'parity': {'oracle_sample_reads': int(len(sample)), 'oracle_mismatches': int(mism),
+                          'reads_with_status': int((~ok).sum()),
+                          'reads_exact_vs_truth': float(np.mean(len2[ok] == truth_all[ok])) if ok.any() else 0.0,
+                          'gathered_everything': bool((status >= 0).all()),
+                          'len2_checksum': checksum,
+                          'len2_checksum_note': 'sum((id+1)*len2) mod 2^61-1 over all reads: identical at every N '
+                                                'because the reads do not depend on the sharding'}}
+    del d_sig, eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
@@ -228,36 +348,49 @@ def main():
     from warpstr_b200.automata import StateAutomata
     from warpstr_b200.caller import CallerEngine
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    # ---- host-side preparation, before CUDA exists in this process (the process pools below fork) ----------
+    locus = synth.make_locus(args.locus, seed=1)
+    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    sig, off, lengths, rev, truth = synth.make_read_batch(locus, args.reads, seed=1000 * CONFIG_ID + rank)
+    n_states = np.array([stas[0].n_states, stas[1].n_states])
+    n_edges = np.array([stas[0].n_edges, stas[1].n_edges])
 
-    # CPU baseline first (rank 0, single-GPU runs only), before the GPU is busy
+    # the oracle over the first reads of the batch (rank 0): compared with the GPU's results further down
+    n_parity = args.parity_reads if args.parity_reads >= 0 else (10000 if world == 1 else 2000)
+    n_parity = min(n_parity, args.reads)
+    parity_want = None
+    if rank == 0 and n_parity > 0:
+        from oracle import bulk
+        parity_want = bulk.run_reads([locus.template_regex, locus.reverse_regex], locus.flank_length,
+                                     [sig[o:o + n] for o, n in zip(off[:n_parity], lengths[:n_parity])],
+                                     rev[:n_parity].astype(int), rev[:n_parity].astype(bool), workers=cores)
+
+    # CPU baseline (rank 0, single-GPU runs only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = args.cpu_reads or 2 * cores
-        locus0 = synth.make_locus(args.locus, seed=1)
-        sample = synth.make_reads(locus0, n_cpu, seed=1000 * CONFIG_ID)
+        sample = synth.make_reads(locus, n_cpu, seed=1000 * CONFIG_ID)
         pool = CpuPool(args.locus, 1, cores, 'port')
         pool.run([r.signal for r in sample[:cores]], [r.reverse for r in sample[:cores]])   # warm the workers
         dt, cpu_len = pool.run([r.signal for r in sample], [r.reverse for r in sample])
         pool.close()
-        s0 = [StateAutomata(locus0.template_regex).n_states, StateAutomata(locus0.reverse_regex).n_states]
-        cells = float(sum(2 * len(r.signal) * s0[int(r.reverse)] for r in sample))
+        cells = float(sum(2 * len(r.signal) * n_states[int(r.reverse)] for r in sample))
         cpu_baseline = {'value': n_cpu / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'mcups': cells / dt / 1e6,
                         'sample': f'{n_cpu} reads of the same workload; ' + CPU_SAMPLE_NOTE['port'] +
                                   ' (`--impl reference` times the unmodified reference itself)'}
 
-    locus = synth.make_locus(args.locus, seed=1)
-    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    legs = [leg_prepare(name, args, max(1, min(8, cores // max(world, 1))))
+            for name in args.legs.split(',') if name in LEG_SPECS]
+
+    # ---- device ---------------------------------------------------------------------------------------------
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     eng = CallerEngine()
     ids = [eng.add_automaton(s, locus.flank_length) for s in stas]
-    sig, off, lengths, rev, truth = synth.make_read_batch(locus, args.reads, seed=1000 * CONFIG_ID + rank)
     aut = np.where(rev > 0, ids[1], ids[0]).astype(np.int32)
     host = torch.from_numpy(sig).pin_memory()
-    n_states = np.array([stas[0].n_states, stas[1].n_states])
-    n_edges = np.array([stas[0].n_edges, stas[1].n_edges])
     cells_pass = float((lengths.astype(np.int64) * n_states[rev.astype(np.int64)]).sum())
     alg_ops_pass = float((lengths.astype(np.int64) *
                           (4 * n_states[rev.astype(np.int64)] + 5 * n_edges[rev.astype(np.int64)])).sum())
@@ -287,20 +420,42 @@ def main():
             res['gathered_len2'] = g['len2'].cpu().numpy()
         return res
 
-    # parity spot check of the benchmark batch itself (a few reads against the oracle, rank 0)
+    # parity of the benchmark batch itself: its first n_parity reads against the oracle (rank 0)
     o = step_resident()
     torch.cuda.synchronize()
     status = o['status'].cpu().numpy()
+    len1 = o['len1'].cpu().numpy()
     len2 = o['len2'].cpu().numpy()
+    cost1, cost2 = o['cost1'].cpu().numpy(), o['cost2'].cpu().numpy()
+    ties = o['ties'].cpu().numpy()
     n_fallback = int((status != 0).sum())
-    if rank == 0:
-        from oracle import caller_oracle as co
-        tbs = [co.tables_from(s) for s in stas]
-        for r in range(3):
-            x = sig[off[r]:off[r] + lengths[r]]
-            want = co.run_read(x, tbs[int(rev[r])], locus.flank_length, bool(rev[r]), impl='c')
-            assert status[r] != 0 or len(want.resc_seq) == int(len2[r]), 'benchmark batch disagrees with the oracle'
-    exact = float(np.mean(len2[status == 0] == truth[status == 0])) if (status == 0).any() else 0.0
+    parity = {'reads_exact_vs_truth': float(np.mean(len2[status == 0] == truth[status == 0])) if (status == 0).any() else 0.0,
+              'reads_with_status': n_fallback, 'host_fallback_reads': n_fallback + int((ties > 0).sum()),
+              'ttest_tie_reads': int((ties > 0).sum()),
+              'ttest_tie_note': 'reads with a t-test decision within 16 ulp of flipping (d_ttest_ties): the only reads '
+                                "whose bad-repeat mask can depend on the host libm's pow rounding"}
+    if parity_want is not None:
+        seq1, seq2, soff = o['seq1'].cpu().numpy(), o['seq2'].cpu().numpy(), o['seq_off']
+        mism = {'len': 0, 'seq': 0, 'cost': 0, 'status': 0}
+        for r, w in enumerate(parity_want):
+            if w[0] == 'error':
+                mism['status'] += int(status[r] == 0)
+                continue
+            if status[r] != 0:
+                mism['status'] += 1
+                continue
+            if ties[r] > 0:
+                continue
+            a = int(soff[r])
+            mism['len'] += int(len1[r] != len(w[0]) or len2[r] != len(w[1]))
+            mism['seq'] += int(seq1[a:a + len1[r]].tobytes().decode() != w[0] or seq2[a:a + len2[r]].tobytes().decode() != w[1])
+            mism['cost'] += int(cost1[r] != w[2] or cost2[r] != w[3])
+        parity['oracle_reads'] = len(parity_want)
+        parity['oracle_mismatches'] = mism
+        parity['oracle_note'] = ('every one of these reads through the oracle (DP in C, numpy/scipy mid-stage, Pool on the '
+                                 'host cores): allele lengths, sequences and both state-wise costs compared bit for bit')
+        assert not any(mism.values()), f'benchmark batch disagrees with the oracle: {mism}'
+        del seq1, seq2
 
     fp64_rate = _lib.measure_fp64_add_rate()
 
@@ -348,6 +503,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- strong-scaling legs through the sharded call ------------------------------------------------------
+    inf = [eng.automata[i].info() for i in ids]
+    del d_sig, host, o, res
+    eng = None
+    gc.collect()
+    torch.cuda.empty_cache()
+    leg_out = {}
+    for leg in legs:
+        leg_out[leg['name']] = leg_run(leg, args, rank, world, barrier)
+
     if rank == 0:
         total_reads = args.reads * world
         fill = prof['dp_fill_traceback']
@@ -369,7 +534,6 @@ def main():
         # FP64-pipe instructions the kernel executes per DP row of one read: per lane 5 DADD per chain slot,
         # 4 + candidates per generic slot, one DSETP per candidate = 4 K + 2 NB (K slots per lane, NB = direction
         # bits per lane and row = candidates), times 32 lanes
-        inf = [eng.automata[i].info() for i in ids]
         fp64_per_row = float(np.mean([32 * (4 * a['states_per_lane'] + 2 * a['dir_bits_per_row']) for a in inf]))
         rows_pass = float(lengths.astype(np.int64).sum())
         secs = fill_ms_launch * 1e-3
@@ -418,9 +582,9 @@ def main():
                                  'algorithmic_bytes_per_launch': alg_bytes}},
             'cpu_baseline': cpu_baseline,
             'clocks': clocks,
-            'parity': {'reads_exact_vs_truth': exact, 'host_fallback_reads': n_fallback,
-                       'oracle_spot_check': 'first 3 reads bit-exact'},
+            'parity': parity,
         }
+        line.update({k: v for k, v in leg_out.items() if v is not None})
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

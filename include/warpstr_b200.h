@@ -151,6 +151,7 @@ typedef struct {
     double max_std;                 /* rescaling.max_std */
     int32_t method;                 /* rescaling.method: 0 mean, 1 median */
     int32_t reps_as_one;            /* rescaling.reps_as_one: must be 0 here */
+    int64_t ttest_guard_ulps;       /* width of the d_ttest_ties test in units in the last place; 0 = 16 */
 } wstr_call_params;
 
 typedef struct {
@@ -165,6 +166,11 @@ typedef struct {
     int32_t *d_trace1;      /* optional: first-pass trace, same offsets as the signal */
     int32_t *d_trace2;      /* optional: second-pass trace */
     double *d_rescaled;     /* optional: rescaled signal, same offsets as the signal */
+    int32_t *d_ttest_ties;  /* optional: per read, the number of t-test decisions of mask_bad_repeats
+                             * (caller.py:347-378) within 16 ulp of flipping.  The reference squares with
+                             * libm's pow (np.float64 ** 2), which may differ from x*x in the last bit; a read
+                             * with 0 ties is decided identically whatever the libm, a read with ties > 0 should
+                             * be re-evaluated where the reference's libm is (the Python layer does). */
 } wstr_call_outputs;
 
 /* workspace for processing the whole batch in one wave; anything >= the size for the largest

@@ -376,6 +376,71 @@ def mask_bad_repeats(x: np.ndarray, rep_mask, trace: np.ndarray, trans: np.ndarr
 
 
 # --------------------------------------------------------------------------------------
+# bulk variants: the same arithmetic on array slices / whole windows instead of Python lists
+# per sample, ~3x faster per read; pinned against the functions above (and so against the
+# reference) by tests/test_oracle_golden.py::test_bulk_oracle_equals_the_plain_one
+# --------------------------------------------------------------------------------------
+def create_alignment_bulk(trace: np.ndarray, x: np.ndarray, tb: Tables, kn: Knobs) -> List[RunStat]:
+    if kn.reps_as_one:
+        return create_alignment(trace, x, tb, kn)
+    cut = np.flatnonzero(trace[1:] != trace[:-1]) + 1
+    starts = np.concatenate(([0], cut))
+    ends = np.concatenate((cut, [len(trace)]))
+    return [RunStat(x[a:b], tb.values[trace[a]], _collapse(kn, x[a:b])) for a, b in zip(starts, ends)]
+
+
+def _tstats_bulk(data: np.ndarray, win: int) -> List[float]:
+    """t statistic at every centre of `data` (caller.py:347-354, 358): np.mean / np.std of 3 samples are
+    sequential sums; the squares are libm pow(x, 2.0) -- what `np.float64 ** 2` evaluates to."""
+    from math import pow as libm_pow
+    assert win == 3
+    n = len(data) - 2 * win + 1
+    if n <= 0:
+        return []
+    w = np.lib.stride_tricks.sliding_window_view(data, win)          # w[c] = data[c:c+3]
+
+    mean = ((w[:, 0] + w[:, 1]) + w[:, 2]) / 3
+    d = w - mean[:, None]
+    sd = np.sqrt(((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]) / 3)
+    sq = np.fromiter((libm_pow(v, 2.0) for v in sd.tolist()), dtype=np.float64, count=len(sd))
+    den = np.sqrt((sq[:n] + sq[win:win + n]) / win)
+    den = np.where(den == 0, den + 0.0000001, den)
+    return ((mean[:n] - mean[win:win + n]) / den).tolist()
+
+
+def segment_count_bulk(data: np.ndarray, win: int) -> int:
+    stats = _tstats_bulk(data, win)
+    n_borders = 0
+    rising = False
+    prev = stats[0]                       # IndexError on an empty window, like the reference
+    for t in stats:
+        if t > 3 or t < -3:
+            if (t > 3 and t >= prev) or (t < -3 and t <= prev):
+                rising = True
+            else:
+                if rising:
+                    n_borders += 1
+                rising = False
+        elif rising:
+            n_borders += 1
+            rising = False
+        prev = t
+    return n_borders - 1
+
+
+def mask_bad_repeats_bulk(x: np.ndarray, rep_mask, trace: np.ndarray, trans: np.ndarray, kn: Knobs):
+    start, end, lo, hi, bounds = find_event_borders(rep_mask, trace, trans, kn)
+    win = 3
+    counts = [segment_count_bulk(x[bounds[n] - win:b + win], win) for n, b in enumerate(bounds[1:])]
+    out = np.zeros(len(x), dtype=bool)
+    for n, c in enumerate(counts):
+        if c >= kn.states_in_segment + 1:
+            out[bounds[n]:bounds[n + 1]] = True
+    _ = bounds[0]
+    return start, end, out
+
+
+# --------------------------------------------------------------------------------------
 # whole read (caller.py:117-149, 178-187)
 # --------------------------------------------------------------------------------------
 _COMP = str.maketrans('ACGTN', 'TGCAN')
@@ -402,17 +467,20 @@ class OracleResult:
 
 
 def run_read(x: np.ndarray, tb: Tables, flank_length: int, reverse: bool,
-             kn: Optional[Knobs] = None, impl: str = 'rows') -> OracleResult:
+             kn: Optional[Knobs] = None, impl: str = 'rows', bulk: bool = False) -> OracleResult:
+    """``bulk``: the array-slice variants of the mid-stage (same arithmetic, ~3x faster)."""
     kn = kn or Knobs()
     x = np.asarray(x, dtype=np.float64)
+    align = create_alignment_bulk if bulk else create_alignment
+    mask_of = mask_bad_repeats_bulk if bulk else mask_bad_repeats
     t1 = warp(x, tb, None, kn, flank_length, impl)
-    runs1 = create_alignment(t1, x, tb, kn)
+    runs1 = align(t1, x, tb, kn)
     resc = rescale_signal(x, runs1, kn)
-    start, end, bad = mask_bad_repeats(x, tb.rep_mask, t1, state_transitions(t1), kn)
+    start, end, bad = mask_of(x, tb.rep_mask, t1, state_transitions(t1), kn)
     t2 = warp(resc, tb, bad, kn, flank_length, impl)
-    runs2 = create_alignment(t2, resc, tb, kn)
+    runs2 = align(t2, resc, tb, kn)
     resc2 = rescale_signal(resc, runs2, kn)
-    start2, end2, _ = mask_bad_repeats(resc2, tb.rep_mask, t2, state_transitions(t2), kn)
+    start2, end2, _ = mask_of(resc2, tb.rep_mask, t2, state_transitions(t2), kn)
     cost = np.mean([abs(r.state_value - r.expected) for r in runs1[start:end]])
     cost2 = np.mean([abs(r.state_value - r.expected) for r in runs2[start2:end2]])
     return OracleResult(seq=decode_sequence(t1, tb, flank_length, reverse), cost=cost,

@@ -86,3 +86,27 @@ def test_invalid_mv_is_reported(built_lib):
     locus = synth.make_locus('AAAT', seed=1)
     with pytest.raises(_lib.WarpstrError):
         eng.add_automaton(StateAutomata(locus.template_regex), 110)
+
+
+def test_ttest_tie_guard_sends_reads_to_the_host_libm(built_lib, oracle_c):
+    """d_ttest_ties: with the default width (16 ulp) no read of a batch is flagged; with an absurd width
+    every read is, takes the host evaluation (the host's own pow decides, as in the reference) and still
+    agrees with the oracle."""
+    from warpstr_b200.caller import CallerEngine
+    locus = synth.make_locus('HD', seed=70)
+    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    reads = synth.make_reads(locus, 6, seed=71, noise=0.3)
+    want = [co.run_read(r.signal, co.tables_from(stas[int(r.reverse)]), 110, r.reverse, impl='c') for r in reads]
+    for width, flagged in ((0, 0), (1 << 51, len(reads))):
+        eng = CallerEngine()
+        eng.ttest_guard_ulps = width
+        ids = [eng.add_automaton(s, 110) for s in stas]
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            res = eng.call_batch([r.signal for r in reads], [ids[int(r.reverse)] for r in reads],
+                                 [r.reverse for r in reads])
+        assert eng.last_ttest_ties == flagged
+        for g, w in zip(res, want):
+            assert g.seq == w.seq and g.resc_seq == w.resc_seq
+            assert g.cost == w.cost and g.resc_cost == w.resc_cost

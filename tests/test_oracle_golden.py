@@ -41,6 +41,20 @@ def test_caller_oracle_matches_reference_goldens(caller_gold, oracle_c, impl):
         assert got.cost == case['cost'] and got.resc_cost == case['resc_cost'], k
 
 
+def test_bulk_oracle_equals_the_plain_one(caller_gold, oracle_c):
+    """run_read(bulk=True) -- array slices and whole-window t statistics instead of per-sample Python
+    lists, what the 10^3..10^4-read parity checks use -- gives the reference's goldens bit for bit."""
+    z, cases = caller_gold
+    for case in cases:
+        k = case['key']
+        got = co.run_read(z[f'{k}_signal'], _tables(case), case['flank'], case['reverse'], impl='c', bulk=True)
+        T = len(got.trace1)
+        assert np.array_equal(got.badmask, np.unpackbits(z[f'{k}_ref_badmask'])[:T].astype(bool)), k
+        assert np.array_equal(got.trace2, z[f'{k}_ref_trace2']), k
+        assert got.seq == case['seq'] and got.resc_seq == case['resc_seq'], k
+        assert got.cost == case['cost'] and got.resc_cost == case['resc_cost'], k
+
+
 def test_fill_matrices_bit_identical(caller_gold, oracle_c):
     z, cases = caller_gold
     for case in cases[:6]:

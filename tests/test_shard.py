@@ -103,3 +103,46 @@ def test_chunk_schedule_of_the_pipelined_call():
                     assert sizes.max() <= 12500 and sizes[-1] <= 6250
                 else:
                     assert sizes.max() == 25000
+
+
+def _worker_by_id(rank, world, port, n_total, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from warpstr_b200.shard import gather_by_id
+        costs = (np.arange(n_total) % 11 + 1) * 1000.0
+        shards = partition_reads(costs, world)
+        if world == 2:                       # unequal shards: move a few reads over
+            shards = [np.concatenate((shards[0], shards[1][:5])), shards[1][5:]]
+        mine = shards[rank]
+        t = torch.from_numpy(mine)
+        out = gather_by_id(t, (t * 3).int(), (t * 3 + 1).int(), (t % 2).int(), t * 0.5, t * 0.25,
+                           [len(s) for s in shards], n_total + 2)
+        want = np.arange(n_total)
+        ok = (np.array_equal(out['len1'][:n_total].numpy(), want * 3) and
+              np.array_equal(out['len2'][:n_total].numpy(), want * 3 + 1) and
+              np.array_equal(out['status'][:n_total].numpy(), want % 2) and
+              np.array_equal(out['cost1'][:n_total].numpy(), want * 0.5) and
+              np.array_equal(out['cost2'][:n_total].numpy(), want * 0.25) and
+              (out['len2'][n_total:].numpy() == -1).all() and np.isnan(out['cost2'][n_total:].numpy()).all())
+        q.put((rank, bool(ok), len(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_by_id_two_ranks_gloo():
+    """The panel's gather: unequal shards, ids scattered over the batch, reads nobody owns stay -1/NaN."""
+    world, n_total = 2, 101
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_by_id, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(ok for _, ok, _ in res)
+    assert sum(n for _, _, n in res) == n_total

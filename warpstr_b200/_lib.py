@@ -29,14 +29,16 @@ c_vp = ctypes.c_void_p
 class CallParams(ctypes.Structure):
     _fields_ = [('min_values_per_state', ctypes.c_int32), ('states_in_segment', ctypes.c_int32),
                 ('threshold', ctypes.c_double), ('max_std', ctypes.c_double),
-                ('method', ctypes.c_int32), ('reps_as_one', ctypes.c_int32)]
+                ('method', ctypes.c_int32), ('reps_as_one', ctypes.c_int32),
+                ('ttest_guard_ulps', ctypes.c_int64)]
 
 
 class CallOutputs(ctypes.Structure):
     _fields_ = [('d_len1', ctypes.c_void_p), ('d_len2', ctypes.c_void_p), ('d_cost1', ctypes.c_void_p),
                 ('d_cost2', ctypes.c_void_p), ('d_status', ctypes.c_void_p), ('d_seq1', ctypes.c_void_p),
                 ('d_seq2', ctypes.c_void_p), ('seq_off', ctypes.POINTER(ctypes.c_int64)),
-                ('d_trace1', ctypes.c_void_p), ('d_trace2', ctypes.c_void_p), ('d_rescaled', ctypes.c_void_p)]
+                ('d_trace1', ctypes.c_void_p), ('d_trace2', ctypes.c_void_p), ('d_rescaled', ctypes.c_void_p),
+                ('d_ttest_ties', ctypes.c_void_p)]
 
 
 _SIGNATURES = {
@@ -267,7 +269,8 @@ def call_workspace_bytes(automata: Sequence[DeviceAutomaton], read_automaton, le
 
 def call_batch(automata: Sequence[DeviceAutomaton], read_automaton, read_reverse, d_signal, sig_off, lengths,
                params: CallParams, d_workspace, d_len1, d_len2, d_cost1, d_cost2, d_status, d_seq1=None,
-               d_seq2=None, seq_off=None, d_trace1=None, d_trace2=None, d_rescaled=None, stream=None) -> None:
+               d_seq2=None, seq_off=None, d_trace1=None, d_trace2=None, d_rescaled=None, stream=None,
+               d_ttest_ties=None) -> None:
     ra = _np(read_automaton, np.int32)
     rv = _np(read_reverse, np.uint8)
     so = _np(sig_off, np.int64)
@@ -275,7 +278,7 @@ def call_batch(automata: Sequence[DeviceAutomaton], read_automaton, read_reverse
     qo = _np(seq_off, np.int64) if seq_off is not None else None
     out = CallOutputs(_dptr(d_len1), _dptr(d_len2), _dptr(d_cost1), _dptr(d_cost2), _dptr(d_status),
                       _dptr(d_seq1), _dptr(d_seq2), _ptr(qo, c_i64p) if qo is not None else None,
-                      _dptr(d_trace1), _dptr(d_trace2), _dptr(d_rescaled))
+                      _dptr(d_trace1), _dptr(d_trace2), _dptr(d_rescaled), _dptr(d_ttest_ties))
     rc = lib().wstr_call_batch(
         _handles(automata), len(automata), _ptr(ra, c_i32p), _ptr(rv, c_u8p), _dptr(d_signal), _ptr(so, c_i64p),
         _ptr(ln, c_i32p), int(ln.shape[0]), ctypes.byref(params), _dptr(d_workspace),

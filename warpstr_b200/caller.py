@@ -35,6 +35,8 @@ class WarpResult:
         return self.trace[keep]
 
 
+_SCALARS = ('len1', 'len2', 'cost1', 'cost2', 'status', 'ties')      # per-read results of a call
+
 # exception types the reference raises for a read, by d_status code
 _STATUS_ERRORS = {
     1: (IndexError, 'index out of bounds: signal shorter than min_values_per_state + 1'),
@@ -107,6 +109,8 @@ class CallerEngine:
         self._host_out = None
         self._dev_cache = {}
         self._h2d_probe = None
+        self.ttest_guard_ulps = 0    # 0 = the library's default (16 ulp), see wstr_call_outputs.d_ttest_ties
+        self.last_ttest_ties = 0     # reads of the last results_from() that were re-evaluated for a t-test tie
 
     # -- automata ------------------------------------------------------------------------
     def add_automaton(self, sta, flank_length: int) -> int:
@@ -240,13 +244,16 @@ class CallerEngine:
             if into is not None:      # caller-owned result buffers (views of the right sizes)
                 o = dict(into)
                 o['status'].zero_()
+                if 'ties' in o:
+                    o['ties'].zero_()
             else:
                 o = dict(
                     len1=torch.empty(n, dtype=torch.int32, device=self.device),
                     len2=torch.empty(n, dtype=torch.int32, device=self.device),
                     cost1=torch.empty(n, dtype=torch.float64, device=self.device),
                     cost2=torch.empty(n, dtype=torch.float64, device=self.device),
-                    status=torch.zeros(n, dtype=torch.int32, device=self.device))
+                    status=torch.zeros(n, dtype=torch.int32, device=self.device),
+                    ties=torch.zeros(n, dtype=torch.int32, device=self.device))
             seq_off = None
             if want_seq:
                 cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
@@ -263,10 +270,10 @@ class CallerEngine:
                 o['rescaled'] = torch.empty(d_sig.numel(), dtype=torch.float64, device=self.device)
             params = _lib.CallParams(self.cc.min_values_per_state, self.cc.states_in_segment,
                                      float(self.rc.threshold), float(self.rc.max_std),
-                                     1 if self.rc.method == 'median' else 0, 0)
+                                     1 if self.rc.method == 'median' else 0, 0, int(self.ttest_guard_ulps))
             _lib.call_batch(self.automata, aut, rev, d_sig, off, lengths, params, ws, o['len1'], o['len2'],
                             o['cost1'], o['cost2'], o['status'], o.get('seq1'), o.get('seq2'), seq_off,
-                            o.get('trace1'), o.get('trace2'), o.get('rescaled'))
+                            o.get('trace1'), o.get('trace2'), o.get('rescaled'), d_ttest_ties=o.get('ties'))
         return o
 
     def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True,
@@ -303,7 +310,7 @@ class CallerEngine:
             d_sig = self._device_buffer('sig', min(total, host_signal.numel()), torch.float64)
             dev = {k: self._device_buffer(k, n, dt) for k, dt in
                    (('len1', torch.int32), ('len2', torch.int32), ('cost1', torch.float64),
-                    ('cost2', torch.float64), ('status', torch.int32))}
+                    ('cost2', torch.float64), ('status', torch.int32), ('ties', torch.int32))}
             if want_seq:
                 dev['seq1'] = self._device_buffer('seq1', int(seq_off[-1]), torch.uint8)
                 dev['seq2'] = self._device_buffer('seq2', int(seq_off[-1]), torch.uint8)
@@ -356,7 +363,7 @@ class CallerEngine:
                 with torch.cuda.stream(st):
                     st.wait_event(ev)
                     mark(f'call{a} begin', st)
-                    into = {k: dev[k][a:b] for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+                    into = {k: dev[k][a:b] for k in _SCALARS}
                     if want_seq:
                         into['seq1'] = dev['seq1'][int(seq_off[a]):int(seq_off[b])]
                         into['seq2'] = dev['seq2'][int(seq_off[a]):int(seq_off[b])]
@@ -367,7 +374,7 @@ class CallerEngine:
                     done.record(st)
                 with torch.cuda.stream(cs_out):                 # results back while the next chunk computes
                     cs_out.wait_event(done)
-                    for k in ('len1', 'len2', 'cost1', 'cost2', 'status'):
+                    for k in _SCALARS:
                         out[k][a:b].copy_(o[k], non_blocking=True)
                     if want_seq:
                         s0, s1 = int(seq_off[a]), int(seq_off[b])
@@ -383,7 +390,8 @@ class CallerEngine:
         # per-read scalars are handed back as copies; reads the device could not finish (status != 0) carry
         # -1 / NaN instead of whatever the buffers held.  The sequence bytes are views of the engine's pinned
         # buffers (hundreds of MB per 100 000 reads): valid until the next call_arrays on this engine.
-        res = {k: out[k][:n].numpy().copy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+        res = {k: out[k][:n].numpy().copy() for k in _SCALARS}
+        res['ttest_ties'] = res.pop('ties')
         bad = res['status'] != 0
         if bad.any():
             res['len1'][bad] = -1
@@ -455,6 +463,7 @@ class CallerEngine:
                        cost1=torch.empty(n_cap, dtype=torch.float64, pin_memory=pin),
                        cost2=torch.empty(n_cap, dtype=torch.float64, pin_memory=pin),
                        status=torch.empty(n_cap, dtype=torch.int32, pin_memory=pin),
+                       ties=torch.empty(n_cap, dtype=torch.int32, pin_memory=pin),
                        seq1=torch.empty(s_cap, dtype=torch.uint8, pin_memory=pin),
                        seq2=torch.empty(s_cap, dtype=torch.uint8, pin_memory=pin))
             self._host_out = cur
@@ -464,6 +473,8 @@ class CallerEngine:
         """Device results -> CallerResult list; reads the device could not finish (status != 0)
         are redone on the host path or raise what the reference raises."""
         status = o['status'].cpu().numpy()
+        ties = o['ties'].cpu().numpy() if 'ties' in o else np.zeros_like(status)
+        self.last_ttest_ties = int((ties > 0).sum())
         len1, len2 = o['len1'].cpu().numpy(), o['len2'].cpu().numpy()
         cost1, cost2 = o['cost1'].cpu().numpy(), o['cost2'].cpu().numpy()
         seq1, seq2 = o['seq1'].cpu().numpy(), o['seq2'].cpu().numpy()
@@ -471,7 +482,9 @@ class CallerEngine:
         out: List[Optional[CallerResult]] = []
         redo = []
         for r in range(len(status)):
-            if status[r] == 0:
+            # (a read with a t-test decision within rounding distance of flipping is decided by the libm the
+            # reference runs on -- np.float64 ** 2 is pow(), caller.py:351 -- so it is evaluated on the host)
+            if status[r] == 0 and ties[r] == 0:
                 a = int(off[r])
                 out.append(CallerResult(seq=seq1[a:a + len1[r]].tobytes().decode('ascii'), cost=float(cost1[r]),
                                         resc_seq=seq2[a:a + len2[r]].tobytes().decode('ascii'),

@@ -971,6 +971,8 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     mp.pad_ = 0;
     mp.threshold = params->threshold;
     mp.max_std = params->max_std;
+    mp.ties = out->d_ttest_ties;
+    mp.tie_ulps = params->ttest_guard_ulps > 0 ? params->ttest_guard_ulps : 16;
     if (int zrc = zero_counters(d_queue, 64, s)) return zrc;
     wstr_prof_begin(1, s);
     rc = wstr_launch_midstage(mp, false, s);
@@ -984,6 +986,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     mp.trace = d_trace2;
     mp.rescaled = nullptr;
     mp.maskbits = nullptr;
+    mp.ties = nullptr;
     mp.len = out->d_len2;
     mp.cost = out->d_cost2;
     mp.seq = out->d_seq2;

@@ -270,8 +270,15 @@ __device__ __forceinline__ double tstat_of(double ma, double sa, double mb, doub
 // x[c-3:c] with x[c:c+3]; the right window of position c is the left window of c+3, so its mean
 // and deviation are kept for three positions instead of being computed twice.
 // GUARD = false: every sample of the read is `tame`, the divisions by 3 need no range test.
+//
+// `ties` counts the decisions that sit within `tie_ulps` units in the last place of flipping: |t| against
+// 3 and, beyond 3, t against its predecessor.  The reference squares the two deviations with pow(x, 2)
+// (np.float64 ** 2, caller.py:351), and a libm pow that is not correctly rounded (glibc >= 2.28: < 1 ULP)
+// returns the neighbour of x*x for ~0.1 % of arguments; that moves t by at most ~3 ulp.  A read without
+// ties is therefore decided identically whatever the libm; a read with ties is reported (d_ttest_ties)
+// and the Python layer re-evaluates it with the host's own pow.
 template <bool GUARD>
-__device__ int count_segments(const double *__restrict__ x, int c0, int c1) {
+__device__ int count_segments(const double *__restrict__ x, int c0, int c1, const long long tie_ulps, int &ties) {
     const Divisor three = make_divisor(3.0);
     int borders = 0;
     bool rising = false;
@@ -291,6 +298,18 @@ __device__ int count_segments(const double *__restrict__ x, int c0, int c1) {
         m2 = mb; s2 = sb;
         const double t = tstat_of<GUARD>(ma, sa, mb, sb, three);
         if (c == c0) prev = t;
+        {
+            const long long at = __double_as_longlong(fabs(t)), three_bits = 0x4008000000000000LL;
+            long long d3 = at - three_bits;
+            d3 = d3 < 0 ? -d3 : d3;
+            bool tie = d3 <= tie_ulps;
+            if (!tie && c != c0 && at >= three_bits - tie_ulps && ((t > 0.0) == (prev > 0.0))) {
+                long long dp = at - __double_as_longlong(fabs(prev));
+                dp = dp < 0 ? -dp : dp;
+                tie = dp <= tie_ulps;
+            }
+            ties += tie ? 1 : 0;
+        }
         if (t > 3.0 || t < -3.0) {
             if ((t > 3.0 && t >= prev) || (t < -3.0 && t <= prev)) {
                 rising = true;
@@ -667,13 +686,15 @@ __global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
             const int nwords = (T + 31) >> 5;
             for (int w = lane; w < nwords; w += 32) mw[w] = 0u;
             __syncwarp();
+            int ties = 0;
             for (int n0 = 0; n0 < nb - 1; n0 += 32) {
                 const int n = n0 + lane;
                 if (n < nb - 1) {
                     const int b_lo = run_start[ra + n * p.sis + 1] - 1;
                     const int b_hi = run_start[ra + (n + 1) * p.sis + 1] - 1;
                     const int c1 = min(b_hi, T - 3);
-                    const int segs = tt_fast ? count_segments<false>(x, b_lo, c1) : count_segments<true>(x, b_lo, c1);
+                    const int segs = tt_fast ? count_segments<false>(x, b_lo, c1, p.tie_ulps, ties)
+                                             : count_segments<true>(x, b_lo, c1, p.tie_ulps, ties);
                     if (segs >= p.sis + 1) {
                         for (int w = b_lo >> 5; w <= (b_hi - 1) >> 5; ++w) {
                             const int lo = max(b_lo, w << 5), hi = min(b_hi, (w + 1) << 5);   // [lo, hi)
@@ -684,6 +705,10 @@ __global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
                         }
                     }
                 }
+            }
+            if (p.ties) {
+                for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(FULL, ties, o);
+                if (lane == 0) p.ties[rd.read] = ties;
             }
         }
 

@@ -121,6 +121,8 @@ struct MidParams {
     int32_t mv, sis;
     int32_t method, pad_;        // 0 mean, 1 median (state value of a run)
     double threshold, max_std;
+    int32_t *ties;               // may be NULL: t-test decisions within tie_ulps of flipping, per read (first pass)
+    long long tie_ulps;
 };
 
 int wstr_launch_midstage(const MidParams &p, bool second, cudaStream_t s);

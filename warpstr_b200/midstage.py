@@ -11,6 +11,7 @@ This is the host path of the engine (``engine='host'``) and the fallback for
 rescaler configurations the GPU mid-stage does not cover (``reps_as_one``,
 ``method: median``, splines that need interior knots).
 """
+import math
 from dataclasses import dataclass
 
 import numpy as np
@@ -108,7 +109,12 @@ def _tstats(x: np.ndarray, lo: int, hi: int) -> np.ndarray:
 
     ma, sa = stats(a)
     mb, sb = stats(b)
-    sd = np.sqrt((sa * sa + sb * sb) / 3)
+    # the reference squares numpy scalars, `np.std(a) ** 2` (caller.py:351): that is libm's pow(x, 2.0),
+    # which need not be x*x in the last bit -- use the host's pow so that a tie is decided as the
+    # reference decides it on this machine
+    sa2 = np.fromiter((math.pow(v, 2.0) for v in sa.tolist()), dtype=np.float64, count=len(sa))
+    sb2 = np.fromiter((math.pow(v, 2.0) for v in sb.tolist()), dtype=np.float64, count=len(sb))
+    sd = np.sqrt((sa2 + sb2) / 3)
     sd = np.where(sd == 0, sd + 0.0000001, sd)
     return (ma - mb) / sd
 

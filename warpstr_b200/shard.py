@@ -98,6 +98,75 @@ def gather_device(len1, len2, status, cost1, cost2, group=None):
     return dict(len1=g_i[:, 0], len2=g_i[:, 1], status=g_i[:, 2], cost1=g_f[:, 0], cost2=g_f[:, 1])
 
 
+_SEL_CACHE: dict = {}
+
+
+def _all_gather_rows(t, world, group=None):
+    """[world, *t.shape] with every rank's ``t`` (same shape everywhere)."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    if t.device.type == 'cuda':
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), t.contiguous(), group=group)
+    return out
+
+
+def gather_by_id(ids, len1, len2, status, cost1, cost2, counts: Sequence[int], n_total: int, group=None):
+    """Id-keyed gather of the per-read results of unequal shards, entirely on the tensors' device and
+    without a host synchronisation: ``counts`` (every rank's shard size) is known to all ranks from the
+    deterministic partition, so nothing has to be asked.  Two collectives (16 + 16 B per read, padded to
+    the largest shard); every rank returns batch-ordered tensors (len1, len2, status int32; cost1, cost2
+    float64; -1 / NaN where no rank reported a read)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    assert len(counts) == world
+    dev = ids.device
+    n_local = int(ids.shape[0])
+    cap = int(max(counts)) if len(counts) else 0
+    ints = torch.full((cap, 4), -1, dtype=torch.int32, device=dev)
+    flts = torch.full((cap, 2), float('nan'), dtype=torch.float64, device=dev)
+    if n_local:
+        ints[:n_local] = torch.stack((ids.to(torch.int32), len1, len2, status), dim=1)
+        flts[:n_local] = torch.stack((cost1, cost2), dim=1)
+    if world > 1:
+        g_i = _all_gather_rows(ints, world, group)
+        g_f = _all_gather_rows(flts, world, group)
+    else:
+        g_i, g_f = ints[None], flts[None]
+    # rows that hold a record, as an index list built on the host (a boolean mask would make torch ask
+    # the device for the number of set bits, i.e. synchronise)
+    key = (tuple(int(c) for c in counts), str(dev))
+    sel = _SEL_CACHE.get(key)
+    if sel is None:
+        sel = torch.as_tensor(np.concatenate([r * cap + np.arange(int(c), dtype=np.int64)
+                                              for r, c in enumerate(counts)] or [np.zeros(0, np.int64)]), device=dev)
+        _SEL_CACHE.clear()
+        _SEL_CACHE[key] = sel
+    rows_i = g_i.reshape(-1, 4).index_select(0, sel)
+    rows_f = g_f.reshape(-1, 2).index_select(0, sel)
+    idx = rows_i[:, 0].long()
+    out_i = torch.full((n_total, 3), -1, dtype=torch.int32, device=dev)
+    out_f = torch.full((n_total, 2), float('nan'), dtype=torch.float64, device=dev)
+    out_i.index_copy_(0, idx, rows_i[:, 1:])
+    out_f.index_copy_(0, idx, rows_f)
+    return dict(len1=out_i[:, 0], len2=out_i[:, 1], status=out_i[:, 2], cost1=out_f[:, 0], cost2=out_f[:, 1])
+
+
+def call_sharded_packed(engine, ids, d_sig, off, lengths, aut, rev, counts: Sequence[int], n_total: int,
+                        group=None, d_ids=None):
+    """This rank's shard, already resident on its GPU (``d_sig`` etc. as for ``call_packed``; ``ids`` = the
+    global index of each local read), through the caller and the id-keyed gather.  Asynchronous: nothing
+    here waits for the device."""
+    import torch
+    o = engine.call_packed(d_sig, off, lengths, aut, rev, want_seq=False)
+    if d_ids is None:
+        d_ids = torch.as_tensor(np.asarray(ids, dtype=np.int64), device=d_sig.device)
+    return gather_by_id(d_ids, o['len1'], o['len2'], o['status'], o['cost1'], o['cost2'], counts, n_total, group)
+
+
 def call_sharded(engine, signals: Sequence[np.ndarray], aut_ids: Sequence[int], reverse: Sequence[bool],
                  n_states: Sequence[int], group=None) -> Dict[str, np.ndarray]:
     """Every rank holds the same read list (or at least its own shard's signals), calls its

@@ -199,3 +199,93 @@ def make_read_batch(locus: SynthLocus, n: int, seed: int = 0, noise: float = 0.1
     else:
         out = np.concatenate((sig, np.zeros(2)))
     return out, offsets, lengths, rev, truth
+
+
+# ---------------------------------------------------------------------------------------------------
+# Multi-locus panels: many loci, a fixed number of reads each, sharded over the GPUs
+# of a box.  A locus's reads are `base_reads` noiseless (allele, dwell) realisations, each used
+# reads_per_locus / base_reads times with its own Gaussian noise.  The noise is drawn on the GPU from a
+# generator seeded per locus and laid out over ALL reads of the locus in read order, so a read's samples
+# do not depend on how the panel is sharded: N ranks and one rank see bit-identical reads.
+# ---------------------------------------------------------------------------------------------------
+PANEL_MIX = ('AAAT', 'HD', 'FMR1', 'FMR1_MGG', 'DM2', 'CAN', 'RFC1', 'C9ORF72_100', 'HD', 'FMR1')
+
+
+def make_panel(n_loci: int, seed: int = 0, patterns: Tuple[str, ...] = PANEL_MIX) -> List[SynthLocus]:
+    """``n_loci`` loci cycling through ``patterns``, each with its own random flanks."""
+    return [make_locus(f'{patterns[i % len(patterns)]}_{i}', seed=seed * 1000 + i, recipe=patterns[i % len(patterns)])
+            for i in range(n_loci)]
+
+
+def _panel_base_one(args):
+    locus, base_reads, seed = args
+    return make_read_batch(locus, base_reads, seed=seed, noise=0.0)
+
+
+def make_panel_base(loci: List[SynthLocus], base_reads: int, seed: int = 0, workers: int = 1):
+    """Noiseless base reads of every locus: list of (signal, offsets, lengths, reverse, truth_len).
+    ``workers`` > 1 spreads the loci over forked processes (call it before CUDA is initialised)."""
+    jobs = [(loc, base_reads, seed * 7919 + i) for i, loc in enumerate(loci)]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(min(workers, len(jobs))) as pool:
+            return pool.map(_panel_base_one, jobs, chunksize=1)
+    return [_panel_base_one(j) for j in jobs]
+
+
+def panel_read_table(base, reads_per_locus: int):
+    """Per read of the panel (global id = locus * reads_per_locus + k): locus, base read, length, strand."""
+    n_loci = len(base)
+    B = len(base[0][2])
+    k = np.arange(reads_per_locus, dtype=np.int64)
+    bidx = np.tile(k % B, n_loci)
+    locus = np.repeat(np.arange(n_loci, dtype=np.int64), reads_per_locus)
+    lengths = np.concatenate([b[2][k % B] for b in base]).astype(np.int32)
+    rev = np.concatenate([b[3][k % B] for b in base]).astype(np.uint8)
+    truth = np.concatenate([b[4][k % B] for b in base]).astype(np.int32)
+    return locus, bidx, lengths, rev, truth
+
+
+def materialize_panel_reads(base, reads_per_locus: int, ids: np.ndarray, noise: float, seed: int, device):
+    """Signals of the panel reads ``ids`` (ascending global ids) on ``device``: float64, concatenated with
+    even starts.  Returns (d_sig, offsets int64[n], lengths int32[n])."""
+    import torch
+    ids = np.asarray(ids, dtype=np.int64)
+    n_loci = len(base)
+    B = len(base[0][2])
+    loc_of = ids // reads_per_locus
+    k_of = ids % reads_per_locus
+    lengths = np.empty(len(ids), dtype=np.int32)
+    for L in range(n_loci):
+        sel = loc_of == L
+        if sel.any():
+            lengths[sel] = base[L][2][k_of[sel] % B]
+    padded = (lengths.astype(np.int64) + 1) & ~1
+    offsets = np.zeros(len(ids), dtype=np.int64)
+    offsets[1:] = np.cumsum(padded[:-1])
+    total = int(padded.sum()) + 2
+    d_sig = torch.zeros(total, dtype=torch.float64, device=device)
+    kall = np.arange(reads_per_locus, dtype=np.int64)
+    for L in range(n_loci):
+        sel = np.flatnonzero(loc_of == L)
+        if not len(sel):
+            continue
+        bsig, boff, blen = base[L][0], base[L][1], base[L][2]
+        all_len = blen[kall % B].astype(np.int64)              # every read of the locus, in read order
+        cum = np.zeros(reads_per_locus + 1, dtype=np.int64)
+        cum[1:] = np.cumsum(all_len)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(int(seed) * 1000003 + L)
+        z = torch.randn(int(cum[-1]), generator=gen, dtype=torch.float64, device=device)
+        d_base = torch.from_numpy(bsig).to(device)
+        ks = k_of[sel]
+        ln = torch.from_numpy(all_len[ks]).to(device)
+        rep = torch.repeat_interleave(torch.arange(len(sel), device=device), ln)
+        first = torch.cumsum(ln, 0) - ln
+        t = torch.arange(int(ln.sum().item()), device=device) - first[rep]
+        src = torch.from_numpy(boff[ks % B]).to(device)[rep] + t
+        nz = torch.from_numpy(cum[ks]).to(device)[rep] + t
+        dst = torch.from_numpy(offsets[sel]).to(device)[rep] + t
+        d_sig[dst] = d_base[src] + noise * z[nz]
+        del z, d_base, rep, t, src, nz, dst
+    return d_sig, offsets, lengths
