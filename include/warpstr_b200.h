@@ -178,6 +178,12 @@ typedef struct {
 int64_t wstr_call_workspace_bytes(wstr_automaton *const *automata, int32_t n_automata,
                                   const int32_t *read_automaton, const int32_t *lengths,
                                   int32_t n_reads);
+/* The smallest workspace wstr_call_batch accepts for this batch: everything that is per batch (rescaled
+ * signal, traces, masks, mid-stage scratch: ~35 B per sample) plus the direction codes of its longest
+ * read.  A caller whose memory cannot hold that cuts the batch into several calls. */
+int64_t wstr_call_workspace_min_bytes(wstr_automaton *const *automata, int32_t n_automata,
+                                      const int32_t *read_automaton, const int32_t *lengths,
+                                      int32_t n_reads);
 /* read_reverse[r] != 0: the read is on the reverse strand (its sequence is reverse-complemented,
  * caller.py:187).  Other arguments as for wstr_warp_batch. */
 int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,

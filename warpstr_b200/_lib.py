@@ -66,6 +66,8 @@ _SIGNATURES = {
     'wstr_measure_fp64_add_rate': (ctypes.c_int, [c_f64p, c_vp]),
     'wstr_call_workspace_bytes': (ctypes.c_int64, [ctypes.POINTER(c_vp), ctypes.c_int32, c_i32p, c_i32p,
                                                    ctypes.c_int32]),
+    'wstr_call_workspace_min_bytes': (ctypes.c_int64, [ctypes.POINTER(c_vp), ctypes.c_int32, c_i32p, c_i32p,
+                                                       ctypes.c_int32]),
     'wstr_call_batch': (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int32, c_i32p, c_u8p, c_vp, c_i64p, c_i32p,
                                        ctypes.c_int32, ctypes.POINTER(CallParams), c_vp, ctypes.c_int64,
                                        ctypes.POINTER(CallOutputs), c_vp]),
@@ -264,6 +266,16 @@ def call_workspace_bytes(automata: Sequence[DeviceAutomaton], read_automaton, le
                                         int(ln.shape[0]))
     if n < 0:
         check(int(n), 'wstr_call_workspace_bytes')
+    return int(n)
+
+
+def call_workspace_min_bytes(automata: Sequence[DeviceAutomaton], read_automaton, lengths) -> int:
+    ra = _np(read_automaton, np.int32)
+    ln = _np(lengths, np.int32)
+    n = lib().wstr_call_workspace_min_bytes(_handles(automata), len(automata), _ptr(ra, c_i32p), _ptr(ln, c_i32p),
+                                            int(ln.shape[0]))
+    if n < 0:
+        check(int(n), 'wstr_call_workspace_min_bytes')
     return int(n)
 
 

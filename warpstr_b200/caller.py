@@ -235,9 +235,15 @@ class CallerEngine:
     def call_packed(self, d_sig, off, lengths, aut, rev, want_seq: bool = True, want_debug: bool = False,
                     into: Optional[dict] = None, lane: int = 0):
         """wstr_call_batch on device-resident signals.  Returns a dict of device tensors
-        (len1, len2, cost1, cost2, status[, seq1, seq2, seq_off])."""
+        (len1, len2, cost1, cost2, status, ties[, seq1, seq2, seq_off]).  A batch whose per-batch buffers
+        (rescaled signal, traces, mid-stage scratch: ~35 B per sample) do not fit the workspace the memory
+        allows is cut into consecutive slices, one library call each."""
         import torch
         n = len(lengths)
+        lengths = np.asarray(lengths, dtype=np.int32)
+        off = np.asarray(off, dtype=np.int64)
+        aut = np.asarray(aut, dtype=np.int32)
+        rev = np.asarray(rev, dtype=np.uint8)
         with torch.cuda.device(self.device):
             need = _lib.call_workspace_bytes(self.automata, aut, lengths)
             ws = self._workspace(need, lane)
@@ -271,10 +277,42 @@ class CallerEngine:
             params = _lib.CallParams(self.cc.min_values_per_state, self.cc.states_in_segment,
                                      float(self.rc.threshold), float(self.rc.max_std),
                                      1 if self.rc.method == 'median' else 0, 0, int(self.ttest_guard_ulps))
-            _lib.call_batch(self.automata, aut, rev, d_sig, off, lengths, params, ws, o['len1'], o['len2'],
-                            o['cost1'], o['cost2'], o['status'], o.get('seq1'), o.get('seq2'), seq_off,
-                            o.get('trace1'), o.get('trace2'), o.get('rescaled'), d_ttest_ties=o.get('ties'))
+            for a, b in self._slices(ws.numel(), need, aut, lengths):
+                lo = int(off[a])
+                hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel()) if b > a else lo
+                sl = slice(lo, hi)
+
+                def part(key, x0, x1):
+                    t = o.get(key)
+                    return t[x0:x1] if t is not None else None
+                s0 = int(seq_off[a]) if want_seq else 0
+                _lib.call_batch(self.automata, aut[a:b], rev[a:b], d_sig[sl], off[a:b] - lo, lengths[a:b], params, ws,
+                                o['len1'][a:b], o['len2'][a:b], o['cost1'][a:b], o['cost2'][a:b], o['status'][a:b],
+                                part('seq1', s0, None), part('seq2', s0, None),
+                                seq_off[a:b] - s0 if want_seq else None,
+                                part('trace1', lo, hi), part('trace2', lo, hi), part('rescaled', lo, hi),
+                                d_ttest_ties=o['ties'][a:b] if 'ties' in o else None)
         return o
+
+    def _slices(self, ws_bytes: int, need: int, aut, lengths):
+        """Consecutive read ranges of one call_packed: the whole batch when the workspace holds what a call
+        needs per batch (the direction codes may still go in waves), else slices that leave half of the
+        workspace to the direction codes."""
+        n = len(lengths)
+        if n == 0:
+            return []
+        if need <= ws_bytes or _lib.call_workspace_min_bytes(self.automata, aut, lengths) <= ws_bytes // 2:
+            return [(0, n)]
+        parts = 2
+        while True:
+            cum = np.cumsum(lengths.astype(np.int64))
+            cuts = np.searchsorted(cum, cum[-1] * np.arange(1, parts) / parts, side='right')
+            bounds = sorted(set([0] + [int(c) for c in cuts] + [n]))
+            pairs = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+            if all(_lib.call_workspace_min_bytes(self.automata, aut[a:b], lengths[a:b]) <= ws_bytes // 2
+                   for a, b in pairs) or parts >= n:
+                return pairs
+            parts *= 2
 
     def call_arrays(self, host_signal, off, lengths, aut, rev, want_seq: bool = True,
                     chunk_reads: int = 25000, lanes: int = 2) -> Dict[str, np.ndarray]:

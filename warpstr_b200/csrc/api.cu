@@ -866,6 +866,20 @@ extern "C" int64_t wstr_call_workspace_bytes(wstr_automaton *const *automata, in
     return (int64_t)c.o_dir + words * 4 + 256;
 }
 
+extern "C" int64_t wstr_call_workspace_min_bytes(wstr_automaton *const *automata, int32_t n_automata,
+                                                 const int32_t *read_automaton, const int32_t *lengths,
+                                                 int32_t n_reads) {
+    if (!automata || n_automata <= 0 || n_reads < 0 || !lengths) return WSTR_ERR_INVALID_ARGUMENT;
+    int64_t widest = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        const int a = read_automaton ? read_automaton[r] : 0;
+        if (a < 0 || a >= n_automata) return WSTR_ERR_INVALID_ARGUMENT;
+        widest = std::max(widest, dir_words(automata[a], lengths[r]));
+    }
+    const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true);
+    return (int64_t)c.o_dir + widest * 4 + 256;
+}
+
 extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,
                                const int32_t *read_automaton, const uint8_t *read_reverse,
                                const double *d_signal, const int64_t *sig_off, const int32_t *lengths,
