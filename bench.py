@@ -255,12 +255,19 @@ def leg_run(leg, args, rank, world, barrier):
     for _ in range(max(3, args.warmup if args.warmup < 4 else 3)):
         g = step()
     barrier()
+    from warpstr_b200 import _lib
+    _lib.profile_enable(True)
+    _lib.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host = time.perf_counter()
     e0.record()
     for _ in range(args.leg_steps):
         g = step()
     e1.record()
+    t_host = time.perf_counter() - t_host
     barrier()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,6 +294,9 @@ def leg_run(leg, args, rank, world, barrier):
                'path': 'shard.partition_reads (LPT by T*S) -> CallerEngine.call_packed per rank -> shard.gather_by_id '
                        '(id-keyed NCCL all_gather, 32 B/read)',
                'shard_reads': counts, 'shard_load_imbalance': float(loads.max() / loads.mean()),
+               'rank0_kernel_ms_per_step': {k: prof[k]['ms'] / args.leg_steps for k in ('dp_fill_traceback', 'midstage', 'plan_upload')},
+               'rank0_launches_per_step': {k: prof[k]['launches'] / args.leg_steps for k in ('dp_fill_traceback', 'midstage')},
+               'rank0_host_enqueue_ms_per_step': 1e3 * t_host / args.leg_steps,
                'parity': {'oracle_sample_reads': int(len(sample)), 'oracle_mismatches': int(mism),
                           'reads_with_status': int((~ok).sum()),
                           'reads_exact_vs_truth': float(np.mean(len2[ok] == truth_all[ok])) if ok.any() else 0.0,

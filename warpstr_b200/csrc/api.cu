@@ -627,14 +627,48 @@ int plan_fill(wstr_automaton *const *automata, int n_automata, const int32_t *re
     int32_t *order = reinterpret_cast<int32_t *>(block + bl.o_order);
     for (int a = 0; a < n_automata; ++a) h_auts[a] = automata[a]->dev;
 
-    // longest reads first
+    // longest reads first, equal lengths in batch order: a counting sort over the lengths (a comparison
+    // sort of a million reads is tens of milliseconds of host time in front of every call)
     std::vector<int> idx(n_reads);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lengths[x] > lengths[y]; });
+    int maxlen = 0;
+    for (int r = 0; r < n_reads; ++r) maxlen = std::max(maxlen, (int)lengths[r]);
+    if (maxlen <= (1 << 22)) {
+        std::vector<int> pos((size_t)maxlen + 2, 0);
+        for (int r = 0; r < n_reads; ++r) pos[lengths[r]]++;
+        int run = 0;
+        for (int l = maxlen; l >= 0; --l) {       // first slot of each length, longest first
+            const int c = pos[l];
+            pos[l] = run;
+            run += c;
+        }
+        for (int r = 0; r < n_reads; ++r) idx[pos[lengths[r]]++] = r;
+    } else {
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lengths[x] > lengths[y]; });
+    }
+
+    // kernel shape class of every automaton
+    std::vector<int> cls_of(n_automata), cls_rep, cls_spad;
+    for (int a = 0; a < n_automata; ++a) {
+        const DevAutomaton &d = automata[a]->dev;
+        int c = -1;
+        for (size_t k = 0; k < cls_rep.size(); ++k) {
+            const DevAutomaton &o = automata[cls_rep[k]]->dev;
+            if (o.KC == d.KC && o.KG == d.KG && o.DEG == d.DEG) c = (int)k;
+        }
+        if (c < 0) {
+            c = (int)cls_rep.size();
+            cls_rep.push_back(a);
+            cls_spad.push_back(0);
+        }
+        cls_spad[c] = std::max(cls_spad[c], (int)d.spad);
+        cls_of[a] = c;
+    }
+    const int n_classes = (int)cls_rep.size();
+    std::vector<int> cls_first, cls_count, cls_order;
 
     waves.clear();
     int cursor = 0;
-    std::vector<char> done;
     while (cursor < n_reads) {
         const int wave_begin = cursor;
         int64_t used = 0;
@@ -655,33 +689,35 @@ int plan_fill(wstr_automaton *const *automata, int n_automata, const int32_t *re
             ++cursor;
         }
         if (cursor == wave_begin) return WSTR_ERR_WORKSPACE_TOO_SMALL;   // one read does not fit
-        // one launch per kernel shape (chain slots, generic slots, in-degree) present in this wave
+        // one launch per kernel shape (chain slots, generic slots, in-degree) present in this wave, shapes in
+        // order of first appearance, the reads of a shape in wave order (longest first): two passes over the
+        // wave with the automata's shape classes looked up from a small table
         Wave w;
         const int nw = cursor - wave_begin;
-        done.assign(nw, 0);
+        cls_first.assign(n_classes, -1);
+        cls_count.assign(n_classes, 0);
+        cls_order.clear();
+        for (int i = 0; i < nw; ++i) {
+            const int c = cls_of[meta[wave_begin + i].aut];
+            if (cls_count[c]++ == 0) cls_order.push_back(c);
+        }
         int filled = wave_begin;
-        for (int i0 = 0; i0 < nw; ++i0) {
-            if (done[i0]) continue;
-            const DevAutomaton &ref = automata[meta[wave_begin + i0].aut]->dev;
+        for (int c : cls_order) {
+            const DevAutomaton &ref = automata[cls_rep[c]]->dev;
             FillLaunch fl;
             fl.kc = ref.KC;
             fl.kg = ref.KG;
             fl.deg = ref.DEG;
-            fl.spad_max = 0;
+            fl.spad_max = cls_spad[c];
             fl.begin = filled;
-            for (int i = i0; i < nw; ++i) {
-                const DevAutomaton &o = automata[meta[wave_begin + i].aut]->dev;
-                if (!done[i] && o.KC == ref.KC && o.KG == ref.KG && o.DEG == ref.DEG) {
-                    order[filled++] = wave_begin + i;
-                    done[i] = 1;
-                    fl.spad_max = std::max(fl.spad_max, (int)o.spad);
-                }
-            }
-            fl.n = filled - fl.begin;
+            fl.n = cls_count[c];
             fl.counter = (int)w.launches.size();
             if (fl.counter >= kCounters) return WSTR_ERR_UNSUPPORTED;
             w.launches.push_back(fl);
+            cls_first[c] = filled;
+            filled += cls_count[c];
         }
+        for (int i = 0; i < nw; ++i) order[cls_first[cls_of[meta[wave_begin + i].aut]]++] = wave_begin + i;
         waves.push_back(std::move(w));
     }
     return WSTR_OK;
