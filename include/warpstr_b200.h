@@ -72,6 +72,19 @@ int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off, const int
                          double *d_out, const int64_t *out_off, double *d_shift_scale,
                          void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- (2b) reads that are already normalised, shipped compactly -----------------------------------
+ * Fast5.get_data_processed ends with `(data - shift) / scale` on the spike-filtered int16 samples
+ * (src/schemas/fast5.py:113); a caller that holds those int16 window samples and the read's
+ * {shift, scale} (e.g. from wstr_normalize_batch's d_shift_scale) can hand them over instead of the
+ * float64 window -- 2 instead of 8 bytes per sample across PCIe -- and gets the same bits:
+ * d_out[out_off[r] + t] = ((double)d_raw[raw_off[r] + t] - shift_r) / scale_r, t < lengths[r].
+ * d_shift_scale: device, {shift, scale} per read.  Reads whose raw_off is a multiple of 8 and out_off
+ * even take the vector path. */
+int64_t wstr_dequantize_workspace_bytes(int32_t n_reads);
+int wstr_dequantize_batch(const int16_t *d_raw, const int64_t *raw_off, const int32_t *lengths,
+                          const double *d_shift_scale, int32_t n_reads, double *d_out,
+                          const int64_t *out_off, void *d_workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- (3) DTW state automaton ----------------------------------------------------------------
  * wstr_automaton_create uploads one strand's automaton: the flat form of StateAutomata
  * (src/caller/automata.py:36-48).  All arrays are host pointers.

@@ -46,3 +46,19 @@ def test_bundled_caller_only_genotype(built_lib):
     np.testing.assert_allclose([r.resc_cost for r in res], z['cost2'], rtol=1e-9)
     # the two alleles the reference's README reports for this test
     assert sorted(set(len(r.resc_seq) for r in res)) == [40, 44]
+
+
+def test_bundled_reads_device_resident_chain(built_lib):
+    """CallerWrapper.run_raw: the same ten reads as DAC counts in, calls out -- normalisation kernel and
+    caller chained on the device (wrapper.get_workload + run, wrapper.py:44-54,104-120), the float64
+    windows never on the host.  Same sequences, lengths and costs as the fixture."""
+    from warpstr_b200.wrapper import CallerWrapper, Locus, flanks_from_template
+    z, raws, wins = _fixture()
+    locus = Locus(name='Human_STR_1108232', sequence=str(z['sequence']), flank_length=int(z['flank_length']))
+    cw = CallerWrapper(locus, threads=2, flanks=flanks_from_template(str(z['left']), str(z['right'])))
+    res = cw.run_raw(raws, wins, [bool(r) for r in z['reverse']])
+    assert [r.resc_seq for r in res] == [str(s) for s in z['resc_seq']]
+    assert [r.seq for r in res] == [str(s) for s in z['seq']]
+    assert [r.cost for r in res] == z['cost1'].tolist()
+    assert [r.resc_cost for r in res] == z['cost2'].tolist()
+    assert sorted(set(len(r.resc_seq) for r in res)) == [40, 44]

@@ -49,6 +49,9 @@ _SIGNATURES = {
     'wstr_normalize_workspace_bytes': (ctypes.c_int64, [ctypes.c_int32]),
     'wstr_normalize_batch': (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_i32p, ctypes.c_int32, ctypes.c_int32,
                                             c_vp, c_i64p, c_vp, c_vp, ctypes.c_int64, c_vp]),
+    'wstr_dequantize_workspace_bytes': (ctypes.c_int64, [ctypes.c_int32]),
+    'wstr_dequantize_batch': (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_vp, ctypes.c_int32, c_vp, c_i64p, c_vp,
+                                             ctypes.c_int64, c_vp]),
     'wstr_automaton_create': (ctypes.c_int, [c_f64p, c_i32p, c_i32p, c_i32p, c_u8p, c_u8p, ctypes.c_int32,
                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.POINTER(c_vp)]),
@@ -251,6 +254,16 @@ def normalize_batch(d_raw, raw_off, win_lo, win_hi, spike_mode: int, d_out, out_
         _dptr(d_out), _ptr(oo, c_i64p), _dptr(d_shift_scale), _dptr(d_workspace),
         int(d_workspace.numel() * d_workspace.element_size()), _stream_ptr(stream))
     check(rc, 'wstr_normalize_batch')
+
+
+def dequantize_batch(d_raw, raw_off, lengths, d_shift_scale, d_out, out_off, d_workspace, stream=None) -> None:
+    ro = _np(raw_off, np.int64)
+    ln = _np(lengths, np.int32)
+    oo = _np(out_off, np.int64)
+    rc = lib().wstr_dequantize_batch(_dptr(d_raw), _ptr(ro, c_i64p), _ptr(ln, c_i32p), _dptr(d_shift_scale),
+                                     int(ln.shape[0]), _dptr(d_out), _ptr(oo, c_i64p), _dptr(d_workspace),
+                                     int(d_workspace.numel() * d_workspace.element_size()), _stream_ptr(stream))
+    check(rc, 'wstr_dequantize_batch')
 
 
 def measure_fp64_add_rate(stream=None) -> float:

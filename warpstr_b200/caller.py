@@ -83,6 +83,118 @@ def pack_masks(masks: Sequence[np.ndarray]):
     return out, offsets
 
 
+def even_offsets(lengths: np.ndarray):
+    """Element offsets of float64 windows packed with 16-byte aligned starts, and the buffer size."""
+    padded = (lengths.astype(np.int64) + 1) & ~1
+    off = np.zeros(len(lengths), dtype=np.int64)
+    if len(lengths) > 1:
+        off[1:] = np.cumsum(padded[:-1])
+    return off, int(padded.sum()) + 2
+
+
+class _IngestF64:
+    """Host float64 windows (the reference's ReadSignal.signal): copied as they are."""
+
+    def __init__(self, eng, host_signal, off, lengths):
+        self.eng, self.host, self.sig_off, self.lengths = eng, host_signal, off, lengths
+        n = len(lengths)
+        self.total = int(off[-1] + ((int(lengths[-1]) + 1) & ~1) + 2) if n else 0
+        self.h2d_bytes = min(self.total, host_signal.numel()) * 8
+
+    def allocate(self):
+        import torch
+        self.d_sig = self.eng._device_buffer('sig', min(self.total, self.host.numel()), torch.float64)
+
+    def send(self, a, b):
+        lo = int(self.sig_off[a])
+        hi = min(int(self.sig_off[b - 1] + ((int(self.lengths[b - 1]) + 1) & ~1) + 2), self.d_sig.numel())
+        self.d_sig[lo:hi].copy_(self.host[lo:hi], non_blocking=True)
+
+    def prepare(self, a, b, lane):
+        pass
+
+    def fetch(self, a, b, out):
+        pass
+
+    def finish(self, res, out, n):
+        pass
+
+
+class _IngestI16:
+    """Host int16 window samples + {shift, scale} per read; float64 windows are made on the device."""
+
+    def __init__(self, eng, host_raw, raw_off, lengths, host_ss):
+        self.eng, self.host, self.raw_off, self.lengths, self.host_ss = eng, host_raw, raw_off, lengths, host_ss
+        self.sig_off, self.total = even_offsets(lengths)
+        self.h2d_bytes = int(host_raw.numel()) * 2 + int(host_ss.numel()) * 8
+
+    def allocate(self):
+        import torch
+        e = self.eng
+        self.d_sig = e._device_buffer('sig', self.total, torch.float64)
+        self.d_raw = e._device_buffer('raw16', int(self.host.numel()), torch.int16)
+        self.d_ss = e._device_buffer('shift_scale', 2 * len(self.lengths), torch.float64)
+
+    def _raw_range(self, a, b):
+        return int(self.raw_off[a]), min(int(self.raw_off[b - 1] + self.lengths[b - 1]), int(self.host.numel()))
+
+    def send(self, a, b):
+        lo, hi = self._raw_range(a, b)
+        self.d_raw[lo:hi].copy_(self.host[lo:hi], non_blocking=True)
+        self.d_ss[2 * a:2 * b].copy_(self.host_ss.reshape(-1)[2 * a:2 * b], non_blocking=True)
+
+    def prepare(self, a, b, lane):
+        import torch
+        ws = self.eng._device_buffer(f'deq_ws{lane}', 24 * (b - a) + 256, torch.uint8)
+        _lib.dequantize_batch(self.d_raw, self.raw_off[a:b], self.lengths[a:b], self.d_ss[2 * a:2 * b], self.d_sig,
+                              self.sig_off[a:b], ws)
+
+    def fetch(self, a, b, out):
+        pass
+
+    def finish(self, res, out, n):
+        pass
+
+
+class _IngestRaw:
+    """Host int16 whole reads + windows; spike removal, MAD normalisation and slicing on the device."""
+
+    def __init__(self, eng, host_raw, raw_off, lo, hi, lengths, spike_mode):
+        self.eng, self.host, self.raw_off, self.lo, self.hi = eng, host_raw, raw_off, lo, hi
+        self.lengths, self.spike_mode = lengths, spike_mode
+        self.sig_off, self.total = even_offsets(lengths)
+        self.h2d_bytes = int(raw_off[-1]) * 2 if len(raw_off) else 0
+
+    def allocate(self):
+        import torch
+        e = self.eng
+        self.d_sig = e._device_buffer('sig', self.total, torch.float64)
+        self.d_raw = e._device_buffer('raw16', int(self.raw_off[-1]), torch.int16)
+        self.d_ss = e._device_buffer('shift_scale', 2 * len(self.lengths), torch.float64)
+        pin = torch.cuda.is_available()
+        cur = e._host_ss
+        if cur is None or cur.numel() < 2 * len(self.lengths):
+            e._host_ss = torch.empty(max(2 * len(self.lengths), 2), dtype=torch.float64, pin_memory=pin)
+
+    def send(self, a, b):
+        lo, hi = int(self.raw_off[a]), int(self.raw_off[b])
+        self.d_raw[lo:hi].copy_(self.host[lo:hi], non_blocking=True)
+
+    def prepare(self, a, b, lane):
+        import torch
+        n = b - a
+        ws = self.eng._device_buffer(f'norm_ws{lane}', _lib.normalize_workspace_bytes(n), torch.uint8)
+        _lib.normalize_batch(self.d_raw, self.raw_off[a:b + 1], self.lo[a:b], self.hi[a:b], self.spike_mode,
+                             self.d_sig, self.sig_off[a:b], self.d_ss[2 * a:2 * b], ws)
+
+    def fetch(self, a, b, out):
+        self.eng._host_ss[2 * a:2 * b].copy_(self.d_ss[2 * a:2 * b], non_blocking=True)
+
+    def finish(self, res, out, n):
+        res['shift_scale'] = self.eng._host_ss[:2 * n].numpy().reshape(n, 2).copy()
+        res['lengths'] = self.lengths
+
+
 class CallerEngine:
     """Batched two-pass WarpSTR caller on one GPU."""
 
@@ -107,6 +219,7 @@ class CallerEngine:
         self._copy_stream = None
         self.timeline = None      # set to a list to collect (label, CUDA event) pairs from call_arrays
         self._host_out = None
+        self._host_ss = None
         self._dev_cache = {}
         self._h2d_probe = None
         self.ttest_guard_ulps = 0    # 0 = the library's default (16 ulp), see wstr_call_outputs.d_ttest_ties
@@ -325,13 +438,48 @@ class CallerEngine:
 
         len/cost/status come back as fresh arrays (-1 / NaN where ``status`` is not 0 -- a read the
         reference would have raised on, see ``_STATUS_ERRORS``); ``seq1``/``seq2`` are views of pinned
-        buffers the engine reuses, valid until the next ``call_arrays`` on it."""
-        import torch
-        n = len(lengths)
+        buffers the engine reuses, valid until the next ``call_arrays*`` on it.
+
+        This is the float64 form of the reference's seam (``ReadSignal.signal``, 8 B per sample over
+        PCIe); ``call_arrays_quantized`` and ``call_arrays_raw`` take the same reads as int16."""
         lengths = np.asarray(lengths, dtype=np.int32)
         off = np.asarray(off, dtype=np.int64)
+        return self._pipeline(_IngestF64(self, host_signal, off, lengths), lengths, aut, rev, want_seq,
+                              chunk_reads, lanes)
+
+    def call_arrays_quantized(self, host_raw, raw_off, lengths, host_shift_scale, aut, rev, want_seq: bool = True,
+                              chunk_reads: int = 25000, lanes: int = 2) -> Dict[str, np.ndarray]:
+        """The same call for reads held as what determines their float64 bits: the int16 samples of each
+        window (``host_raw[raw_off[r] : raw_off[r] + lengths[r]]``, after spike removal; pinned; starts on
+        multiples of 8 samples for the vector path) and the read's ``{shift, scale}`` (float64 [n, 2], pinned).
+        The device evaluates the reference's ``(data - shift) / scale`` (schemas/fast5.py:113) itself
+        (wstr_dequantize_batch): a quarter of the bytes cross PCIe and the windows are bit-identical."""
+        lengths = np.asarray(lengths, dtype=np.int32)
+        raw_off = np.asarray(raw_off, dtype=np.int64)
+        return self._pipeline(_IngestI16(self, host_raw, raw_off, lengths, host_shift_scale), lengths, aut, rev,
+                              want_seq, chunk_reads, lanes)
+
+    def call_arrays_raw(self, host_raw, raw_off, win_lo, win_hi, aut, rev, spike_removal: str = 'Brute',
+                        want_seq: bool = True, chunk_reads: int = 25000, lanes: int = 2) -> Dict[str, np.ndarray]:
+        """Raw reads in, calls out (the reference's get_workload -> CallerWrapper.run, wrapper.py:44-54,104-120):
+        whole int16 reads ``host_raw[raw_off[r] : raw_off[r+1]]`` and their windows ``[win_lo, win_hi]`` go to
+        the device, are spike-filtered, MAD-normalised and sliced there (wstr_normalize_batch) and called
+        without the float64 windows ever visiting the host.  The result also carries ``shift_scale``."""
+        from .normalize import SPIKE_MODES
+        raw_off = np.asarray(raw_off, dtype=np.int64)
+        lo = np.asarray(win_lo, dtype=np.int32)
+        hi = np.asarray(win_hi, dtype=np.int32)
+        lens = np.diff(raw_off)
+        lengths = np.maximum(np.minimum(hi.astype(np.int64), lens - 1) - lo + 1, 0).astype(np.int32)
+        return self._pipeline(_IngestRaw(self, host_raw, raw_off, lo, hi, lengths, SPIKE_MODES[spike_removal]),
+                              lengths, aut, rev, want_seq, chunk_reads, lanes)
+
+    def _pipeline(self, ingest, lengths, aut, rev, want_seq, chunk_reads, lanes) -> Dict[str, np.ndarray]:
+        import torch
+        n = len(lengths)
         aut = np.asarray(aut, dtype=np.int32)
         rev = np.asarray(rev, dtype=np.uint8)
+        off = ingest.sig_off                                    # float64 windows on the device: even starts
         bounds = self._chunk_bounds(n, max(1, chunk_reads))
         cap = lengths.astype(np.int64) // max(self.cc.min_values_per_state - 1, 1) + 16
         seq_off = np.zeros(n + 1, dtype=np.int64)
@@ -342,10 +490,10 @@ class CallerEngine:
             if self._copy_stream is None:
                 self._copy_stream = (torch.cuda.Stream(), torch.cuda.Stream())
             cs_in, cs_out = self._copy_stream
-            total = int(off[-1] + ((int(lengths[-1]) + 1) & ~1) + 2) if n else 0
             # device-side signal and result buffers live on the engine and only ever grow, so the
             # chunk loop makes no allocator calls
-            d_sig = self._device_buffer('sig', min(total, host_signal.numel()), torch.float64)
+            ingest.allocate()
+            d_sig = ingest.d_sig
             dev = {k: self._device_buffer(k, n, dt) for k, dt in
                    (('len1', torch.int32), ('len2', torch.int32), ('cost1', torch.float64),
                     ('cost2', torch.float64), ('status', torch.int32), ('ties', torch.int32))}
@@ -365,15 +513,13 @@ class CallerEngine:
             mark('start', comp)
 
             def send(a, b):                                     # chunk [a, b) -> device, on the input stream
-                lo = int(off[a])
-                hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel())
                 with torch.cuda.stream(cs_in):
                     mark(f'h2d{a} begin', cs_in)
-                    d_sig[lo:hi].copy_(host_signal[lo:hi], non_blocking=True)
+                    ingest.send(a, b)
                     mark(f'h2d{a} end', cs_in)
                     ev = torch.cuda.Event()
                     ev.record(cs_in)
-                return lo, hi, ev
+                return ev
 
             keep = []
             # every chunk's copy is queued up front (the calls stage their metadata through a
@@ -384,7 +530,7 @@ class CallerEngine:
             sent = [send(a, b) for a, b in chunks]
             h2d_end = torch.cuda.Event(enable_timing=True)
             h2d_end.record(cs_in)
-            self._h2d_probe = (h2d_begin, h2d_end, int(d_sig.numel()) * 8)
+            self._h2d_probe = (h2d_begin, h2d_end, int(ingest.h2d_bytes))
             # chunks alternate between `lanes` compute streams (each with its own workspace): the
             # kernels of consecutive chunks are independent, so one chunk's kernel tails and
             # latency-bound mid-stage overlap the next chunk's DP
@@ -395,12 +541,15 @@ class CallerEngine:
             for st in streams[1:]:
                 st.wait_stream(comp)
             for ci, (a, b) in enumerate(chunks):
-                lo, hi, ev = sent[ci]
+                ev = sent[ci]
                 lane = ci % len(streams)
                 st = streams[lane]
+                lo = int(off[a])
+                hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel())
                 with torch.cuda.stream(st):
                     st.wait_event(ev)
                     mark(f'call{a} begin', st)
+                    ingest.prepare(a, b, lane)                  # int16 forms: the float64 windows are made here
                     into = {k: dev[k][a:b] for k in _SCALARS}
                     if want_seq:
                         into['seq1'] = dev['seq1'][int(seq_off[a]):int(seq_off[b])]
@@ -418,6 +567,7 @@ class CallerEngine:
                         s0, s1 = int(seq_off[a]), int(seq_off[b])
                         out['seq1'][s0:s1].copy_(o['seq1'][:s1 - s0], non_blocking=True)
                         out['seq2'][s0:s1].copy_(o['seq2'][:s1 - s0], non_blocking=True)
+                    ingest.fetch(a, b, out)
                     mark(f'd2h{a} end', cs_out)
                 keep.append(o)
             for st in streams[1:]:
@@ -440,6 +590,7 @@ class CallerEngine:
             res['seq1'] = out['seq1'][:int(seq_off[-1])].numpy()
             res['seq2'] = out['seq2'][:int(seq_off[-1])].numpy()
             res['seq_off'] = seq_off[:-1]
+        ingest.finish(res, out, n)
         return res
 
     def _chunk_bounds(self, n: int, step: int):
@@ -506,6 +657,55 @@ class CallerEngine:
                        seq2=torch.empty(s_cap, dtype=torch.uint8, pin_memory=pin))
             self._host_out = cur
         return cur
+
+    def call_raw_batch(self, raws: Sequence[np.ndarray], windows, aut_ids, reverse,
+                       spike_removal: str = 'Brute') -> List[CallerResult]:
+        """Raw int16 reads and their STR windows in, CallerResults out: the reference's
+        ``get_workload`` + ``CallerWrapper.run`` (wrapper.py:44-54, 104-120) as one device-resident chain
+        (``call_arrays_raw``: normalisation kernel -> caller, the float64 windows never leave the GPU)."""
+        import torch
+        n = len(raws)
+        if n == 0:
+            return []
+        lens = np.fromiter((len(r) for r in raws), dtype=np.int64, count=n)
+        if (lens <= 0).any():
+            raise ValueError('empty raw read')
+        raw_off = np.zeros(n + 1, dtype=np.int64)
+        raw_off[1:] = np.cumsum(lens)
+        host = torch.empty(int(raw_off[-1]), dtype=torch.int16, pin_memory=True)
+        hb = host.numpy()
+        for r, o in zip(raws, raw_off[:-1]):
+            hb[o:o + len(r)] = np.asarray(r, dtype=np.int16)
+        lo = np.array([w[0] for w in windows], dtype=np.int32)
+        hi = np.array([w[1] for w in windows], dtype=np.int32)
+        if (lo < 0).any():
+            raise ValueError('negative window start')
+        aut = np.asarray(aut_ids, dtype=np.int32)
+        rev = np.asarray(reverse, dtype=np.uint8)
+        res = self.call_arrays_raw(host, raw_off, lo, hi, aut, rev, spike_removal)
+        status, ties = res['status'], res['ttest_ties']
+        self.last_ttest_ties = int((ties > 0).sum())
+        out: List[Optional[CallerResult]] = []
+        redo = []
+        so = res['seq_off']
+        for r in range(n):
+            if status[r] == 0 and ties[r] == 0:
+                a = int(so[r])
+                out.append(CallerResult(seq=res['seq1'][a:a + res['len1'][r]].tobytes().decode('ascii'),
+                                        cost=float(res['cost1'][r]),
+                                        resc_seq=res['seq2'][a:a + res['len2'][r]].tobytes().decode('ascii'),
+                                        resc_cost=float(res['cost2'][r])))
+            else:
+                out.append(None)
+                redo.append(r)
+        if redo:        # as in results_from: the reference's exception, or the host's libm for a t-test tie
+            from .normalize import normalize_windows
+            sigs = normalize_windows([raws[r] for r in redo], [windows[r] for r in redo], spike_removal,
+                                     device=str(self.device))
+            fixed = self._call_batch_host(sigs, [aut_ids[r] for r in redo], [reverse[r] for r in redo])
+            for r, f in zip(redo, fixed):
+                out[r] = f
+        return out
 
     def results_from(self, o, signals, aut_ids, reverse) -> List[CallerResult]:
         """Device results -> CallerResult list; reads the device could not finish (status != 0)

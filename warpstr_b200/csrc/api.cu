@@ -522,7 +522,7 @@ struct StageSlot {
     cudaEvent_t done = nullptr;
     bool pending = false;
 };
-constexpr int kStageSlots = 4;
+constexpr int kStageSlots = 8;
 StageSlot g_stage[kStageSlots];
 int g_stage_next = 0;
 std::mutex g_stage_mu;
@@ -579,6 +579,38 @@ int stage_upload(StageSlot *sl, void *d_dst, size_t bytes, cudaStream_t s) {
     sl->pending = true;
     return WSTR_OK;
 }
+
+}  // namespace
+
+// the same staging for the other entry points of the library (aux.cu)
+int wstr_stage_begin(size_t bytes, void **h_ptr, void **token) {
+    StageSlot *sl = nullptr;
+    const int rc = stage_acquire(bytes, &sl);
+    if (rc != WSTR_OK) return rc;
+    *h_ptr = sl->h;
+    *token = sl;
+    return WSTR_OK;
+}
+int wstr_stage_commit(void *token, void *d_dst, size_t bytes, cudaStream_t s) {
+    return stage_upload(static_cast<StageSlot *>(token), d_dst, bytes, s);
+}
+namespace {
+__global__ void zero16_kernel(uint4 *__restrict__ p, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+}  // namespace
+// d 16-byte aligned, bytes a multiple of 16
+int wstr_zero_async(void *d, size_t bytes, cudaStream_t s) {
+    const size_t n16 = bytes / 16;
+    if (n16 == 0) return WSTR_OK;
+    const int grid = (int)std::min<size_t>((n16 + 255) / 256, 148 * 8);
+    zero16_kernel<<<grid, 256, 0, s>>>(static_cast<uint4 *>(d), n16);
+    WSTR_CUDA(cudaGetLastError());
+    return WSTR_OK;
+}
+
+namespace {
 
 inline int64_t dir_words(const wstr_automaton *a, int T) {   // RPW rows share a word per lane (dtw.cu: DirFmt)
     if (a->dev.any) return ((int64_t)T + 3) / 4 * a->dev.spad;   // ... per state in the catch-all (dtw_any.cu)

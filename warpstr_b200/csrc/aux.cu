@@ -12,6 +12,8 @@
 #include <limits.h>
 #include <math.h>
 
+#include <string.h>
+
 #include "wstr_internal.h"
 
 // ------------------------------------------------------------------------------------------
@@ -579,17 +581,29 @@ extern "C" int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off
         off = (off + bytes + 255) / 256 * 256;
         return o;
     };
+    // [queue][raw_off][out_off][win_lo][win_hi]: one block, staged through pinned mapped memory and a copy
+    // kernel (a pipelining caller keeps the DMA engines busy with the next chunk's samples)
     const size_t o_q = take(256), o_ro = take(sizeof(int64_t) * (n_reads + 1)), o_oo = take(sizeof(int64_t) * n_reads),
                  o_lo = take(sizeof(int32_t) * n_reads), o_hi = take(sizeof(int32_t) * n_reads);
+    const size_t block_bytes = off;
     const int grid = norm_grid(n_reads);
     const size_t o_gh = take(0);
     if ((int64_t)(o_gh + (size_t)grid * GBINS * 4) > workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
-    WSTR_CUDA(cudaMemsetAsync(ws + o_q, 0, 256, s));
-    WSTR_CUDA(cudaMemcpyAsync(ws + o_ro, raw_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, s));
-    WSTR_CUDA(cudaMemcpyAsync(ws + o_oo, out_off, sizeof(int64_t) * n_reads, cudaMemcpyHostToDevice, s));
-    WSTR_CUDA(cudaMemcpyAsync(ws + o_lo, win_lo, sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, s));
-    WSTR_CUDA(cudaMemcpyAsync(ws + o_hi, win_hi, sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, s));
-    WSTR_CUDA(cudaMemsetAsync(ws + o_gh, 0, (size_t)grid * GBINS * 4, s));
+    {
+        void *h = nullptr, *token = nullptr;
+        int rc = wstr_stage_begin(block_bytes, &h, &token);
+        if (rc != WSTR_OK) return rc;
+        unsigned char *hb = static_cast<unsigned char *>(h);
+        memset(hb + o_q, 0, 256);
+        memcpy(hb + o_ro, raw_off, sizeof(int64_t) * (n_reads + 1));
+        memcpy(hb + o_oo, out_off, sizeof(int64_t) * n_reads);
+        memcpy(hb + o_lo, win_lo, sizeof(int32_t) * n_reads);
+        memcpy(hb + o_hi, win_hi, sizeof(int32_t) * n_reads);
+        rc = wstr_stage_commit(token, ws, block_bytes, s);
+        if (rc != WSTR_OK) return rc;
+        rc = wstr_zero_async(ws + o_gh, (size_t)grid * GBINS * 4, s);
+        if (rc != WSTR_OK) return rc;
+    }
     NormParams p;
     p.raw = d_raw;
     p.raw_off = reinterpret_cast<const int64_t *>(ws + o_ro);
@@ -610,6 +624,88 @@ extern "C" int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off
     }
     wstr_prof_begin(2, s);
     normalize_kernel<<<grid, NT, sizeof(NormSmem), s>>>(p);
+    wstr_prof_end(s);
+    WSTR_CUDA(cudaGetLastError());
+    return WSTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// (2b) already-normalised reads shipped as what determines their bits: the int16 samples of the
+// window (after spike removal) and the read's {shift, scale}.  out[t] = (raw[t] - shift) / scale is the
+// reference's own expression (schemas/fast5.py:113: one float64 subtraction and one division per sample),
+// so the float64 window is reproduced bit for bit from a quarter of the bytes.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct DeqRead {
+    int64_t raw_off, out_off;
+    int32_t n, pad_;
+};
+
+__global__ void __launch_bounds__(256) dequantize_kernel(const int16_t *__restrict__ raw, const DeqRead *__restrict__ reads,
+                                                         const double *__restrict__ shift_scale, double *__restrict__ out,
+                                                         int n_reads) {
+    // one CTA per read (grid-stride); eight samples per thread and step when the read is 16-byte aligned
+    for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const DeqRead rd = reads[r];
+        const double shift = shift_scale[2 * r], scale = shift_scale[2 * r + 1];
+        const int16_t *__restrict__ src = raw + rd.raw_off;
+        double *__restrict__ dst = out + rd.out_off;
+        const int n = rd.n;
+        int done = 0;
+        if (((rd.raw_off & 7) == 0) && ((rd.out_off & 1) == 0)) {
+            const int n8 = n & ~7;
+            for (int t = threadIdx.x * 8; t < n8; t += blockDim.x * 8) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(src + t);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double a = (double)(int16_t)(w[k] & 0xffffu), b = (double)(int16_t)(w[k] >> 16);
+                    double2 v;
+                    v.x = (a - shift) / scale;
+                    v.y = (b - shift) / scale;
+                    *reinterpret_cast<double2 *>(dst + t + 2 * k) = v;
+                }
+            }
+            done = n8;
+        }
+        for (int t = done + threadIdx.x; t < n; t += blockDim.x) dst[t] = ((double)src[t] - shift) / scale;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t wstr_dequantize_workspace_bytes(int32_t n_reads) {
+    if (n_reads < 0) return WSTR_ERR_INVALID_ARGUMENT;
+    return (int64_t)sizeof(DeqRead) * n_reads + 256;
+}
+
+extern "C" int wstr_dequantize_batch(const int16_t *d_raw, const int64_t *raw_off, const int32_t *lengths,
+                                     const double *d_shift_scale, int32_t n_reads, double *d_out,
+                                     const int64_t *out_off, void *d_workspace, int64_t workspace_bytes, void *stream) {
+    if (!d_raw || !raw_off || !lengths || !d_shift_scale || !d_out || !out_off || !d_workspace || n_reads < 0)
+        return WSTR_ERR_INVALID_ARGUMENT;
+    if (n_reads == 0) return WSTR_OK;
+    if (workspace_bytes < wstr_dequantize_workspace_bytes(n_reads)) return WSTR_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    void *h = nullptr, *token = nullptr;
+    const size_t bytes = sizeof(DeqRead) * (size_t)n_reads;
+    int rc = wstr_stage_begin(bytes, &h, &token);
+    if (rc != WSTR_OK) return rc;
+    DeqRead *hr = static_cast<DeqRead *>(h);
+    for (int r = 0; r < n_reads; ++r) {
+        if (lengths[r] < 0 || raw_off[r] < 0 || out_off[r] < 0) return WSTR_ERR_INVALID_ARGUMENT;
+        hr[r].raw_off = raw_off[r];
+        hr[r].out_off = out_off[r];
+        hr[r].n = lengths[r];
+        hr[r].pad_ = 0;
+    }
+    rc = wstr_stage_commit(token, d_workspace, bytes, s);
+    if (rc != WSTR_OK) return rc;
+    const int grid = n_reads < 148 * 8 ? n_reads : 148 * 8;
+    wstr_prof_begin(2, s);
+    dequantize_kernel<<<grid, 256, 0, s>>>(d_raw, static_cast<const DeqRead *>(d_workspace), d_shift_scale, d_out,
+                                           n_reads);
     wstr_prof_end(s);
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;

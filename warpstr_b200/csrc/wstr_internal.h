@@ -142,6 +142,11 @@ struct wstr_automaton {
 };
 
 int wstr_set_cuda_error(cudaError_t e, const char *where);
+// Host arrays of a call travel through a pinned, device-mapped staging slot and a copy kernel on the
+// caller's stream, never through the DMA engines (api.cu): write `bytes` at *h_ptr, then commit.
+int wstr_stage_begin(size_t bytes, void **h_ptr, void **token);
+int wstr_stage_commit(void *token, void *d_dst, size_t bytes, cudaStream_t s);
+int wstr_zero_async(void *d, size_t bytes, cudaStream_t s);   // by a kernel; d 16-byte aligned, bytes % 16 == 0
 void wstr_prof_begin(int category, cudaStream_t s);
 void wstr_prof_end(cudaStream_t s);
 

@@ -119,6 +119,15 @@ class CallerWrapper:
         aut = [self._rev_id if rv else self._temp_id for rv in reverse]
         return self.engine.call_batch(signals, aut, reverse)
 
+    def run_raw(self, raws: Sequence[np.ndarray], windows, reverse: Sequence[bool],
+                spike_removal: Optional[str] = None) -> List[CallerResult]:
+        """``get_workload`` + ``run`` for reads still in DAC counts (wrapper.py:44-54, 104-120): normalised
+        and called on the device in one chain, order preserved."""
+        reverse = [bool(r) for r in reverse]
+        aut = [self._rev_id if rv else self._temp_id for rv in reverse]
+        return self.engine.call_raw_batch(raws, windows, aut, reverse,
+                                          spike_removal or self.caller_config.spike_removal)
+
     # -- state similarity report (wrapper.py:122-160) ------------------------------------------------
     def check_high_similarity(self, sequence: str):
         diffs = {'template': self.pore_model.get_diffs_for_all(sequence),
@@ -209,15 +218,13 @@ class CallerWrapper:
         return results
 
 
-def get_workload(df_overview, path: str, spike_removal: str = 'Brute') -> List[ReadSignal]:
-    """Reads of the locus with their normalised STR windows (reference: wrapper.py:44-54).
-    The raw int16 signal of every saved read comes from its annotated single-read fast5
+def get_raw_workload(df_overview, path: str):
+    """The saved reads of a locus as they are on disk: (names, reverse flags, raw int16 signals, windows).
+    The raw signal of every saved read comes from its annotated single-read fast5
     (``<locus>/fast5/<run_id>/annot/<read>.fast5``, what the reference's extraction step
     writes) or, for a caller-only run prepared straight from a sequencing run's multi-read
-    files, from the file named in the row's ``fast5_path`` column (see caller_only.py).
-    All reads are spike-filtered, MAD normalised and sliced in one GPU launch."""
+    files, from the file named in the row's ``fast5_path`` column (see caller_only.py)."""
     from .fast5 import raw_signal
-    from .normalize import normalize_windows
     names, revs, raws, wins = [], [], [], []
     has_src = 'fast5_path' in df_overview.columns
     for row in df_overview.itertuples():
@@ -232,6 +239,16 @@ def get_workload(df_overview, path: str, spike_removal: str = 'Brute') -> List[R
             names.append(row.Index)
             revs.append(bool(row.reverse))
             wins.append((int(row.l_start_raw), int(row.r_end_raw)))
+    return names, revs, raws, wins
+
+
+def get_workload(df_overview, path: str, spike_removal: str = 'Brute') -> List[ReadSignal]:
+    """Reads of the locus with their normalised STR windows (reference: wrapper.py:44-54): all reads are
+    spike-filtered, MAD normalised and sliced in one GPU launch and returned as host float64 arrays, which
+    is what the reference's ``ReadSignal`` holds.  ``main_wrapper`` does not take this detour: it hands the
+    raw reads to ``CallerWrapper.run_raw``, which keeps the windows on the device."""
+    from .normalize import normalize_windows
+    names, revs, raws, wins = get_raw_workload(df_overview, path)
     sigs = normalize_windows(raws, wins, spike_removal)
     return [ReadSignal(n, r, s) for n, r, s in zip(names, revs, sigs)]
 
@@ -245,10 +262,14 @@ def main_wrapper(locus: Locus, threads: int = 1, config: Optional[Config] = None
     from .overview import load_overview, store_collapsed, store_results
     overview_path, df_overview = load_overview(locus.path)
     cc = config.caller_config if config is not None else CallerConfig()
-    if workload is None:
-        workload = get_workload(df_overview, locus.path, cc.spike_removal)
     call_wrapper = CallerWrapper(locus, threads, flanks=flanks, config=config, engine=engine)
-    results = call_wrapper.run(workload)
+    if workload is None:
+        # raw int16 reads -> normalisation kernel -> caller, all on the device
+        names, revs, raws, wins = get_raw_workload(df_overview, locus.path)
+        results = call_wrapper.run_raw(raws, wins, revs, cc.spike_removal)
+        workload = [ReadSignal(n, r, None) for n, r in zip(names, revs)]
+    else:
+        results = call_wrapper.run(workload)
     seq_results = [(r.seq, r.resc_seq) for r in results]
     cost_results = [(r.cost, r.resc_cost) for r in results]
     df_overview = store_results(overview_path, df_overview, seq_results, cost_results, locus.path)
