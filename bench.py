@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--parity-reads', type=int, default=-1,
                     help='reads of the batch checked against the oracle (-1: 10000 at N=1, 2000 at N>1)')
+    ap.add_argument('--no-e2e-variants', action='store_true', help='skip the int16 and raw-reads end-to-end variants')
+    ap.add_argument('--raw-reads', type=int, default=25000, help='reads of the raw-reads-in end-to-end variant')
     ap.add_argument('--legs', default='c3,panel',
                     help='extra strong-scaling legs through the sharded call: c3 (FMR1, (MGG), DM2; 100k reads), '
                          'panel (C5: 50 loci x 20k reads); empty = none')
@@ -508,14 +510,147 @@ def main():
     h2d = int(host.numel() * 8)
     d2h = int(sum(v.nbytes for k, v in res.items() if not k.startswith('gathered')))
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device='cuda')
+    # ---- the same batch handed over as int16 (a quarter of the bytes), and the raw-reads-in chain -----------
+    def gather_host(res):
+        if world > 1:
+            ints = torch.from_numpy(np.stack((res['len1'], res['len2'], res['status']), axis=1)).cuda()
+            flts = torch.from_numpy(np.stack((res['cost1'], res['cost2']), axis=1)).cuda()
+            shard.gather_device(ints[:, 0], ints[:, 1], ints[:, 2], flts[:, 0], flts[:, 1])
+
+    def time_e2e(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(args.steps):
+            out = fn()
+        eb.record()
+        barrier()
+        return max(ea.elapsed_time(eb), 1e3 * (time.perf_counter() - t0)), out
+
+    variants = {}
+    if not args.no_e2e_variants:
+        # (a) int16 window samples + {shift, scale}: the SURVEY 8d map norm -> DAC counts, made on the GPU
+        Q_SHIFT, Q_SCALE = 90.8717 * 5.85, 9.8354 * 5.85
+        len_t = torch.from_numpy(lengths.astype(np.int64)).cuda()
+        first = torch.cumsum(len_t, 0) - len_t
+        rep = torch.repeat_interleave(torch.arange(len(lengths), device='cuda'), len_t)
+        tpos = torch.arange(int(len_t.sum().item()), device='cuda') - first[rep]
+        src = torch.from_numpy(off).cuda()[rep] + tpos
+        raw_off = np.zeros(len(lengths), dtype=np.int64)
+        raw_off[1:] = np.cumsum((lengths[:-1].astype(np.int64) + 7) & ~7)
+        dst = torch.from_numpy(raw_off).cuda()[rep] + tpos
+        counts16 = torch.round(d_sig[src] * Q_SCALE + Q_SHIFT)
+        d_raw16 = torch.zeros(int(raw_off[-1] + ((int(lengths[-1]) + 7) & ~7)), dtype=torch.int16, device='cuda')
+        d_raw16[dst] = counts16.to(torch.int16)
+        host16 = torch.empty(d_raw16.numel(), dtype=torch.int16).pin_memory()
+        host16.copy_(d_raw16)
+        host_ss = torch.tensor([[Q_SHIFT, Q_SCALE]] * len(lengths), dtype=torch.float64).pin_memory()
+        # the float64 windows those samples stand for, for the check: the reference's (data - shift) / scale
+        d_q64 = torch.zeros_like(d_sig)
+        # (a tensor divisor: torch turns division by a Python scalar into a multiplication by its reciprocal)
+        d_q64[src] = (counts16 - Q_SHIFT) / torch.full_like(counts16, Q_SCALE)
+        want16 = eng.call_packed(d_q64, off, lengths, aut, rev, want_seq=False)
+        want16 = {k: want16[k].cpu().numpy() for k in ('len1', 'len2', 'cost1', 'cost2', 'status')}
+        q_sample = [d_q64[int(off[r]):int(off[r]) + int(lengths[r])].cpu().numpy() for r in range(0, len(lengths), max(1, len(lengths) // 48))][:48]
+        del d_raw16, d_q64, src, dst, rep, tpos, counts16
+
+        def step_i16():
+            res = eng.call_arrays_quantized(host16, raw_off, lengths, host_ss, aut, rev)
+            gather_host(res)
+            return res
+
+        ms_i16, r16 = time_e2e(step_i16)
+        same = all(np.array_equal(r16[k], want16[k], equal_nan=True) for k in want16)
+        variants['e2e_int16'] = {
+            'ms': ms_i16, 'h2d': int(host16.numel() * 2 + host_ss.numel() * 8),
+            'd2h': int(sum(v.nbytes for v in r16.values() if isinstance(v, np.ndarray))),
+            'api': 'CallerEngine.call_arrays_quantized (pinned int16 window samples + {shift, scale} per read -> '
+                   'wstr_dequantize_batch -> wstr_call_batch -> host arrays)',
+            'workload': 'the same reads in DAC counts, raw = rint((90.8717 + 9.8354 x) 5.85) (SURVEY 8d); the device '
+                        "re-creates the float64 windows with the reference's (data - shift) / scale",
+            'parity': {'all_reads_equal_the_float64_call_on_the_same_windows': bool(same)}}
+        if rank == 0:
+            from oracle import caller_oracle as co
+            tbs = [co.tables_from(s_) for s_ in stas]
+            mism = 0
+            for k, x in enumerate(q_sample):
+                r = k * max(1, len(lengths) // 48)
+                w = co.run_read(x, tbs[int(rev[r])], locus.flank_length, bool(rev[r]), impl='c', bulk=True)
+                mism += int(r16['len2'][r] != len(w.resc_seq) or r16['cost2'][r] != w.resc_cost or r16['len1'][r] != len(w.seq))
+            variants['e2e_int16']['parity'].update(oracle_reads=len(q_sample), oracle_mismatches=mism)
+        assert same, 'int16 ingestion disagrees with the float64 call on the same windows'
+        del host16, r16
+
+        # (b) raw reads in: whole int16 reads (window + 8192 flank-like samples, spikes at 1e-4) -> normalisation
+        # kernel -> caller, windows never on the host.  A quarter of the batch (the generator is the slow part).
+        n_raw = max(1, min(len(lengths), args.raw_reads))
+        PAD = 8192
+        gen = torch.Generator(device='cuda')
+        gen.manual_seed(1000 * CONFIG_ID + 77 + rank)
+        ln = torch.from_numpy(lengths[:n_raw].astype(np.int64)).cuda()
+        full_len = ln + PAD
+        roff = np.zeros(n_raw + 1, dtype=np.int64)
+        roff[1:] = np.cumsum(lengths[:n_raw].astype(np.int64) + PAD)
+        total_raw = int(roff[-1])
+        from warpstr_b200.pore_model import get_pore_model
+        table = torch.from_numpy(np.ascontiguousarray(get_pore_model().table)).cuda()
+        kidx = torch.randint(0, table.numel(), (total_raw // 9 + 2,), generator=gen, device='cuda')
+        full = torch.repeat_interleave(table[kidx], 9)[:total_raw] + 0.15 * torch.randn(total_raw, generator=gen, dtype=torch.float64, device='cuda')
+        rep = torch.repeat_interleave(torch.arange(n_raw, device='cuda'), ln)
+        tpos = torch.arange(int(ln.sum().item()), device='cuda') - (torch.cumsum(ln, 0) - ln)[rep]
+        full[torch.from_numpy(roff[:-1]).cuda()[rep] + PAD // 2 + tpos] = d_sig[torch.from_numpy(off[:n_raw]).cuda()[rep] + tpos]
+        counts = torch.round((90.8717 + 9.8354 * full) * 5.85)
+        spikes = torch.rand(total_raw, generator=gen, device='cuda') < 1e-4
+        counts = torch.where(spikes, torch.where(torch.rand(total_raw, generator=gen, device='cuda') < 0.5, 1500.0, 100.0), counts)
+        host_raw = torch.empty(total_raw, dtype=torch.int16).pin_memory()
+        host_raw.copy_(counts.to(torch.int16))
+        win_lo = np.full(n_raw, PAD // 2, dtype=np.int32)
+        win_hi = (win_lo + lengths[:n_raw] - 1).astype(np.int32)
+        del full, counts, spikes, rep, tpos, kidx
+
+        def step_raw():
+            res = eng.call_arrays_raw(host_raw, roff, win_lo, win_hi, aut[:n_raw], rev[:n_raw], 'Brute')
+            gather_host(res)
+            return res
+
+        ms_raw, rr = time_e2e(step_raw)
+        variants['e2e_raw'] = {
+            'ms': ms_raw, 'reads': n_raw, 'h2d': int(total_raw * 2),
+            'd2h': int(sum(v.nbytes for v in rr.values() if isinstance(v, np.ndarray))),
+            'api': 'CallerEngine.call_arrays_raw (pinned int16 whole reads + windows -> wstr_normalize_batch (Brute spike '
+                   'removal, MAD normalisation, slice) -> wstr_call_batch -> host arrays); the get_workload -> '
+                   'CallerWrapper.run chain of src/caller/wrapper.py:44-54,104-120, windows never on the host',
+            'workload': f'{n_raw} reads of the batch, each embedded in a raw read of T + {PAD} samples (flank-like '
+                        'filler, spikes at 1e-4), SURVEY 8d'}
+        if rank == 0:
+            from oracle import caller_oracle as co
+            from oracle import normalize_oracle as no
+            tbs = [co.tables_from(s_) for s_ in stas]
+            mism, checked = 0, 0
+            for r in range(0, n_raw, max(1, n_raw // 32)):
+                raw = host_raw.numpy()[roff[r]:roff[r + 1]]
+                x = no.get_data_processed(raw, (int(win_lo[r]), int(win_hi[r])), 'Brute')
+                w = co.run_read(x, tbs[int(rev[r])], locus.flank_length, bool(rev[r]), impl='c', bulk=True)
+                mism += int(rr['status'][r] != 0 or rr['len2'][r] != len(w.resc_seq) or rr['cost2'][r] != w.resc_cost)
+                checked += 1
+            variants['e2e_raw']['parity'] = {'oracle_reads': checked, 'oracle_mismatches': mism,
+                                             'note': 'numpy normalisation + oracle call of the same raw reads'}
+        del host_raw, rr
+
+    t = torch.tensor([ms_total, ms_e2e] + [v['ms'] for v in variants.values()], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
+    for i, v in enumerate(variants.values()):
+        v['ms'] = float(t[2 + i])
 
     # ---- strong-scaling legs through the sharded call ------------------------------------------------------
     inf = [eng.automata[i].info() for i in ids]
     del d_sig, host, o, res
+    variants_keep = variants
     eng = None
     gc.collect()
     torch.cuda.empty_cache()
@@ -594,6 +729,11 @@ def main():
             'clocks': clocks,
             'parity': parity,
         }
+        for name, v in variants.items():
+            n_v = v.get('reads', args.reads) * world
+            line[name] = {'value': n_v * args.steps / (v['ms'] * 1e-3), 'unit': UNIT, 'reads_per_gpu': v.get('reads', args.reads),
+                          'h2d_bytes_per_step': v['h2d'], 'd2h_bytes_per_step': v['d2h'], 'api': v['api'],
+                          'workload': v['workload'], 'parity': v.get('parity')}
         line.update({k: v for k, v in leg_out.items() if v is not None})
         print(json.dumps(line))
     if world > 1:
