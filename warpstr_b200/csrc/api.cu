@@ -1,6 +1,8 @@
 // Host side of the C ABI: automaton layout + upload, wave scheduling of the DP passes.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -520,33 +522,75 @@ struct StageSlot {
     void *h = nullptr;
     size_t cap = 0;
     cudaEvent_t done = nullptr;
-    bool pending = false;
+    bool pending = false;     // its upload kernel may still be reading it
+    bool reserved = false;    // handed out by stage_acquire, not yet committed
 };
 constexpr int kStageSlots = 8;
 StageSlot g_stage[kStageSlots];
 int g_stage_next = 0;
 std::mutex g_stage_mu;
+std::vector<void *> g_stage_parked;
+size_t g_stage_parked_bytes = 0;
 
-// a staging slot of at least `bytes`, free to overwrite
+// a staging slot of at least `bytes`, free to overwrite.  A slot whose upload has completed is reused
+// before a fresh one is allocated: pinning host memory costs milliseconds (and serialises in the
+// kernel when several processes do it at once), so in steady state one or two slots do all the work.
 int stage_acquire(size_t bytes, StageSlot **out) {
     std::lock_guard<std::mutex> lock(g_stage_mu);
-    StageSlot &sl = g_stage[g_stage_next];
-    g_stage_next = (g_stage_next + 1) % kStageSlots;
-    if (sl.pending) {
-        WSTR_CUDA(cudaEventSynchronize(sl.done));
-        sl.pending = false;
+    int pick = -1;
+    for (int pass = 0; pass < 2 && pick < 0; ++pass) {
+        for (int i = 0; i < kStageSlots && pick < 0; ++i) {
+            StageSlot &sl = g_stage[i];
+            if (sl.pending && cudaEventQuery(sl.done) == cudaSuccess) sl.pending = false;
+            if (sl.pending || sl.reserved) continue;
+            if (pass == 0 ? sl.cap >= bytes : true) pick = i;   // first a free slot that is large enough, then any free one
+        }
     }
+    if (pick < 0 && getenv("WSTR_DEBUG_TIMING")) {
+        for (int i = 0; i < kStageSlots; ++i)
+            fprintf(stderr, "[wstr stage] slot %d cap %zu pending %d reserved %d query %d\n", i, g_stage[i].cap,
+                    (int)g_stage[i].pending, (int)g_stage[i].reserved,
+                    g_stage[i].done ? (int)cudaEventQuery(g_stage[i].done) : -1);
+    }
+    if (pick < 0) {          // everything in flight: wait for the oldest
+        for (int tries = 0; tries < kStageSlots && pick < 0; ++tries) {
+            const int i = g_stage_next;
+            g_stage_next = (g_stage_next + 1) % kStageSlots;
+            if (!g_stage[i].reserved) pick = i;
+        }
+        if (pick < 0) return WSTR_ERR_INVALID_ARGUMENT;   // more concurrent calls than staging slots
+        WSTR_CUDA(cudaEventSynchronize(g_stage[pick].done));
+        g_stage[pick].pending = false;
+    }
+    StageSlot &sl = g_stage[pick];
     if (sl.cap < bytes) {
-        if (sl.h) cudaFreeHost(sl.h);
+        // cudaFreeHost waits for the whole device: an outgrown buffer is parked and only freed once the
+        // parked ones add up to more than the live one would need anyway (sizes double, so that is rare)
+        if (sl.h) {
+            g_stage_parked.push_back(sl.h);
+            g_stage_parked_bytes += sl.cap;
+        }
         sl.h = nullptr;
         sl.cap = 0;
-        const size_t cap = align_up(bytes + bytes / 4 + 4096, 4096);
+        size_t cap = 1 << 16;
+        while (cap < bytes) cap <<= 1;
+        if (g_stage_parked_bytes > 4 * cap) {
+            for (void *p : g_stage_parked) cudaFreeHost(p);
+            g_stage_parked.clear();
+            g_stage_parked_bytes = 0;
+        }
         WSTR_CUDA(cudaHostAlloc(&sl.h, cap, cudaHostAllocMapped | cudaHostAllocPortable));
         sl.cap = cap;
     }
     if (!sl.done) WSTR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    sl.reserved = true;
     *out = &sl;
     return WSTR_OK;
+}
+
+void stage_release(StageSlot *sl) {   // a reserved slot that will not be committed after all
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    sl->reserved = false;
 }
 
 // work counters are cleared by a kernel, not cudaMemsetAsync: the driver may run a memset on a
@@ -575,8 +619,13 @@ int stage_upload(StageSlot *sl, void *d_dst, size_t bytes, cudaStream_t s) {
     upload_kernel<<<grid, 256, 0, s>>>(static_cast<uint4 *>(d_dst), static_cast<const uint4 *>(d_src), n16);
     wstr_prof_end(s);
     WSTR_CUDA(cudaGetLastError());
-    WSTR_CUDA(cudaEventRecord(sl->done, s));
-    sl->pending = true;
+    const cudaError_t ee = cudaEventRecord(sl->done, s);
+    {
+        std::lock_guard<std::mutex> lock(g_stage_mu);
+        sl->pending = ee == cudaSuccess;
+        sl->reserved = false;
+    }
+    if (ee != cudaSuccess) return wstr_set_cuda_error(ee, "cudaEventRecord(stage)");
     return WSTR_OK;
 }
 
@@ -858,7 +907,10 @@ extern "C" int wstr_warp_batch(wstr_automaton *const *automata, int32_t n_automa
     std::vector<Wave> waves;
     rc = plan_fill(automata, n_automata, read_automaton, sig_off, lengths, d_maskbits ? mask_off : nullptr, n_reads,
                    (workspace_bytes - (int64_t)w.o_dir) / 4, static_cast<unsigned char *>(slot->h), w.bl, waves);
-    if (rc != WSTR_OK) return rc;
+    if (rc != WSTR_OK) {
+        stage_release(slot);
+        return rc;
+    }
     rc = stage_upload(slot, ws + w.o_block, w.bl.bytes, s);
     if (rc != WSTR_OK) return rc;
 
@@ -948,6 +1000,21 @@ extern "C" int64_t wstr_call_workspace_min_bytes(wstr_automaton *const *automata
     return (int64_t)c.o_dir + widest * 4 + 256;
 }
 
+namespace {
+struct HostTimer {      // WSTR_DEBUG_TIMING=1: host milliseconds of the sections of a call, on stderr
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char *what;
+    HostTimer(const char *w) : on(getenv("WSTR_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    void lap(const char *label) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[wstr %s] %s %.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automata,
                                const int32_t *read_automaton, const uint8_t *read_reverse,
                                const double *d_signal, const int64_t *sig_off, const int32_t *lengths,
@@ -982,9 +1049,11 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     unsigned char *d_scratch = ws + c.o_scratch;
 
     // ---- the whole host plan, staged and uploaded in one piece -----------------------------
+    HostTimer timer("call_batch");
     StageSlot *slot = nullptr;
     rc = stage_acquire(c.bl.bytes, &slot);
     if (rc != WSTR_OK) return rc;
+    timer.lap("stage_acquire");
     unsigned char *block = static_cast<unsigned char *>(slot->h);
     MidAutomaton *mauts = reinterpret_cast<MidAutomaton *>(block + c.bl.o_mauts);
     for (int a = 0; a < n_automata; ++a) {
@@ -1017,9 +1086,14 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     std::vector<Wave> waves;
     rc = plan_fill(automata, n_automata, read_automaton, sig_off, lengths, mask_off.data(), n_reads,
                    (workspace_bytes - (int64_t)c.o_dir) / 4, block, c.bl, waves);
-    if (rc != WSTR_OK) return rc;
+    if (rc != WSTR_OK) {
+        stage_release(slot);
+        return rc;
+    }
+    timer.lap("plan");
     rc = stage_upload(slot, d_block, c.bl.bytes, s);
     if (rc != WSTR_OK) return rc;
+    timer.lap("stage_upload");
 
     FillDevice fd;
     fd.auts = reinterpret_cast<const DevAutomaton *>(d_block + c.bl.o_auts);
@@ -1076,5 +1150,6 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     wstr_prof_begin(1, s);
     rc = wstr_launch_midstage(mp, true, s);
     wstr_prof_end(s);
+    timer.lap("launches");
     return rc;
 }

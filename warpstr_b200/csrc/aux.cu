@@ -688,13 +688,14 @@ extern "C" int wstr_dequantize_batch(const int16_t *d_raw, const int64_t *raw_of
     if (n_reads == 0) return WSTR_OK;
     if (workspace_bytes < wstr_dequantize_workspace_bytes(n_reads)) return WSTR_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int r = 0; r < n_reads; ++r)
+        if (lengths[r] < 0 || raw_off[r] < 0 || out_off[r] < 0) return WSTR_ERR_INVALID_ARGUMENT;
     void *h = nullptr, *token = nullptr;
     const size_t bytes = sizeof(DeqRead) * (size_t)n_reads;
     int rc = wstr_stage_begin(bytes, &h, &token);
     if (rc != WSTR_OK) return rc;
     DeqRead *hr = static_cast<DeqRead *>(h);
     for (int r = 0; r < n_reads; ++r) {
-        if (lengths[r] < 0 || raw_off[r] < 0 || out_off[r] < 0) return WSTR_ERR_INVALID_ARGUMENT;
         hr[r].raw_off = raw_off[r];
         hr[r].out_off = out_off[r];
         hr[r].n = lengths[r];

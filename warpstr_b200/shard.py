@@ -160,11 +160,20 @@ def call_sharded_packed(engine, ids, d_sig, off, lengths, aut, rev, counts: Sequ
     """This rank's shard, already resident on its GPU (``d_sig`` etc. as for ``call_packed``; ``ids`` = the
     global index of each local read), through the caller and the id-keyed gather.  Asynchronous: nothing
     here waits for the device."""
+    import os
+    import time
     import torch
+    t0 = time.perf_counter()
     o = engine.call_packed(d_sig, off, lengths, aut, rev, want_seq=False)
+    t1 = time.perf_counter()
     if d_ids is None:
         d_ids = torch.as_tensor(np.asarray(ids, dtype=np.int64), device=d_sig.device)
-    return gather_by_id(d_ids, o['len1'], o['len2'], o['status'], o['cost1'], o['cost2'], counts, n_total, group)
+    g = gather_by_id(d_ids, o['len1'], o['len2'], o['status'], o['cost1'], o['cost2'], counts, n_total, group)
+    if os.environ.get('WSTR_DEBUG_TIMING'):
+        import sys
+        print(f'[wstr call_sharded_packed] call_packed {1e3 * (t1 - t0):.1f} ms, gather_by_id '
+              f'{1e3 * (time.perf_counter() - t1):.1f} ms (host)', file=sys.stderr, flush=True)
+    return g
 
 
 def call_sharded(engine, signals: Sequence[np.ndarray], aut_ids: Sequence[int], reverse: Sequence[bool],
