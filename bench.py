@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--parity-reads', type=int, default=-1,
                     help='reads of the batch checked against the oracle (-1: 10000 at N=1, 2000 at N>1)')
+    ap.add_argument('--generic-only', action='store_true', help='run the catch-all DP kernel (dtw_any.cu) instead of the specialised ones')
+    ap.add_argument('--mv', type=int, default=4, help='tr_calling_config.min_values_per_state')
     ap.add_argument('--no-e2e-variants', action='store_true', help='skip the int16 and raw-reads end-to-end variants')
     ap.add_argument('--raw-reads', type=int, default=25000, help='reads of the raw-reads-in end-to-end variant')
     ap.add_argument('--legs', default='c3,panel',
@@ -375,7 +377,8 @@ def main():
         from oracle import bulk
         parity_want = bulk.run_reads([locus.template_regex, locus.reverse_regex], locus.flank_length,
                                      [sig[o:o + n] for o, n in zip(off[:n_parity], lengths[:n_parity])],
-                                     rev[:n_parity].astype(int), rev[:n_parity].astype(bool), workers=cores)
+                                     rev[:n_parity].astype(int), rev[:n_parity].astype(bool), workers=cores,
+                                     knobs=(args.mv, 6, False, 0.5, 0.5, 'mean'))
 
     # CPU baseline (rank 0, single-GPU runs only)
     cpu_baseline = None
@@ -399,8 +402,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    eng = CallerEngine()
+    from warpstr_b200.config import CallerConfig
+    eng = CallerEngine(CallerConfig(min_values_per_state=args.mv))
+    _lib.set_generic_only(args.generic_only)
     ids = [eng.add_automaton(s, locus.flank_length) for s in stas]
+    _lib.set_generic_only(False)
     aut = np.where(rev > 0, ids[1], ids[0]).astype(np.int32)
     host = torch.from_numpy(sig).pin_memory()
     cells_pass = float((lengths.astype(np.int64) * n_states[rev.astype(np.int64)]).sum())

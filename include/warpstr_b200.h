@@ -163,7 +163,7 @@ typedef struct {
     double threshold;               /* rescaling.threshold */
     double max_std;                 /* rescaling.max_std */
     int32_t method;                 /* rescaling.method: 0 mean, 1 median */
-    int32_t reps_as_one;            /* rescaling.reps_as_one: must be 0 here */
+    int32_t reps_as_one;            /* rescaling.reps_as_one (caller.py:69-79) */
     int64_t ttest_guard_ulps;       /* width of the d_ttest_ties test in units in the last place; 0 = 16 */
 } wstr_call_params;
 

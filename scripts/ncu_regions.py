@@ -3,9 +3,14 @@
 their share of executed instructions and of stall samples, plus the raw-page key metrics."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+sel = []
+if len(sys.argv) > 2 and sys.argv[2].startswith('#'):      # '#n': the n-th kernel of a multi-kernel report
+    sel = ['--launch-skip', sys.argv[2][1:], '--launch-count', '1']
+    del sys.argv[2]
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
+print('kernel:', vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else '?')
 want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
@@ -14,9 +19,9 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'smsp__issue_a
 for i, h in enumerate(hdr):
     if h in want or ('issue_stalled' in h and 'per_issue_active' in h and float(vals[i] or 0) > 0.05):
         print(f'{h:90s} {vals[i]:>16s} {units[i]}')
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; data = rows[2:]
+hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; data = [r for r in rows[2:] if len(r) == len(hdr)]
 stalls = [h for h in hdr if h.startswith('stall_')]
 ti = sum(int(r[ix['Instructions Executed']] or 0) for r in data); ts = sum(int(r[ix['# Samples']] or 0) for r in data)
 print('total inst', ti, 'samples', ts)

@@ -69,12 +69,26 @@ def test_median_method_on_the_device(built_lib, oracle_c, name):
         assert g.cost == w.cost and g.resc_cost == w.resc_cost
 
 
-@pytest.mark.parametrize('rc,engine', [(RescalerConfig(method='median'), 'host'), (RescalerConfig(reps_as_one=True), None)])
+@pytest.mark.parametrize('rc,engine', [(RescalerConfig(method='median'), 'host'), (RescalerConfig(reps_as_one=True), 'host')])
 def test_host_engine_variants(built_lib, oracle_c, rc, engine):
     res, want = _run(CallerConfig(), rc, n=3, engine=engine)
     for g, w in zip(res, want):
         assert g.seq == w.seq and g.resc_seq == w.resc_seq
         assert g.resc_cost == pytest.approx(w.resc_cost, rel=1e-9)
+
+
+@pytest.mark.parametrize('method', ['mean', 'median'])
+@pytest.mark.parametrize('name', ['HD', 'DM2', 'C9ORF72_100'])
+def test_reps_as_one_on_the_device(built_lib, oracle_c, name, method):
+    """rescaling.reps_as_one: one alignment entry per distinct state over all its samples
+    (caller.py:69-79) -- on the device, no host evaluation, bit-equal to the oracle."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('error', RuntimeWarning)          # the host path announces itself with one
+        res, want = _run(CallerConfig(), RescalerConfig(reps_as_one=True, method=method), name=name, n=6, noise=0.25)
+    for g, w in zip(res, want):
+        assert g.seq == w.seq and g.resc_seq == w.resc_seq
+        assert g.cost == w.cost and g.resc_cost == w.resc_cost
 
 
 def test_invalid_mv_is_reported(built_lib):

@@ -324,17 +324,14 @@ class CallerEngine:
 
     def call_batch(self, signals: Sequence[np.ndarray], aut_ids: Sequence[int],
                    reverse: Sequence[bool], engine: Optional[str] = None) -> List[CallerResult]:
-        """WarpSTR.run for a batch (caller.py:117-149).  ``engine='gpu'`` (default for the
-        default rescaling configuration) keeps everything on the device (wstr_call_batch);
-        ``engine='host'`` runs the two DP passes on the GPU and the stage between them in
-        numpy/scipy (needed for ``reps_as_one``)."""
+        """WarpSTR.run for a batch (caller.py:117-149).  ``engine='gpu'`` (the default) keeps everything
+        on the device (wstr_call_batch); ``engine='host'`` runs the two DP passes on the GPU and the
+        stage between them with numpy/scipy on the host -- the evaluation used for reads the device
+        flags (a t-test tie, a spline that needs interior knots, a reference exception)."""
         signals = [np.ascontiguousarray(s, dtype=np.float64) for s in signals]
-        gpu_ok = not self.rc.reps_as_one
-        engine = engine or ('gpu' if gpu_ok else 'host')
+        engine = engine or 'gpu'
         if engine == 'host':
             return self._call_batch_host(signals, aut_ids, reverse)
-        if not gpu_ok:
-            raise _lib.WarpstrError('the device mid-stage covers reps_as_one=False only')
         res = self.call_packed(*self.upload(signals, aut_ids, reverse))
         return self.results_from(res, signals, aut_ids, reverse)
 
@@ -389,7 +386,8 @@ class CallerEngine:
                 o['rescaled'] = torch.empty(d_sig.numel(), dtype=torch.float64, device=self.device)
             params = _lib.CallParams(self.cc.min_values_per_state, self.cc.states_in_segment,
                                      float(self.rc.threshold), float(self.rc.max_std),
-                                     1 if self.rc.method == 'median' else 0, 0, int(self.ttest_guard_ulps))
+                                     1 if self.rc.method == 'median' else 0, 1 if self.rc.reps_as_one else 0,
+                                     int(self.ttest_guard_ulps))
             for a, b in self._slices(ws.numel(), need, aut, lengths):
                 lo = int(off[a])
                 hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel()) if b > a else lo

@@ -115,8 +115,8 @@ struct Split {
     unsigned mv_mask;   // bit mv set = instantiated for that min_values_per_state
 };
 // keep in sync with wstr_launch_fill in dtw.cu
-const Split kSplits[] = {{7, 1, 0x10}, {6, 2, 0x7c}, {8, 1, 0x10}, {4, 4, 0x10}, {8, 2, 0x10},
-                         {6, 4, 0x7c}, {8, 4, 0x10}, {12, 4, 0x10}};
+const Split kSplits[] = {{7, 1, 0x10}, {6, 2, 0x7c}, {8, 1, 0x10}, {4, 4, 0x10}, {7, 2, 0x10}, {8, 2, 0x10},
+                         {6, 4, 0x7c}, {7, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
 
 struct Layout {
     int KC = 0, KG = 0, DEG = 2, n_lanes = 0, n_generic = 0;
@@ -937,7 +937,7 @@ struct CallPlan {
 };
 
 CallPlan plan_call(int n_automata, int n_reads, const int64_t *sig_off, const int32_t *lengths, int mv,
-                   bool own_resc, bool own_trace) {
+                   bool own_resc, bool own_trace, int reps = 0, int s_max = 0) {
     CallPlan c;
     c.extent = 0;
     c.mask_words = 0;
@@ -948,7 +948,7 @@ CallPlan plan_call(int n_automata, int n_reads, const int64_t *sig_off, const in
         c.extent = std::max<int64_t>(c.extent, so + lengths[r] + 2);
         run_off += ((int64_t)lengths[r] + 1) & ~(int64_t)1;
         c.mask_words += (lengths[r] + 31) / 32;
-        c.scratch_bytes += wstr_mid_scratch_bytes(lengths[r], mv);
+        c.scratch_bytes += wstr_mid_scratch_bytes(lengths[r], mv, reps, s_max);
     }
     c.bl = block_layout(n_automata, n_reads, true);
     size_t off = 0;
@@ -982,7 +982,11 @@ extern "C" int64_t wstr_call_workspace_bytes(wstr_automaton *const *automata, in
         if (a < 0 || a >= n_automata) return WSTR_ERR_INVALID_ARGUMENT;
         words += dir_words(automata[a], lengths[r]);
     }
-    const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true);
+    // (sized for rescaling.reps_as_one as well, which needs 8 more bytes per sample of scratch: the
+    // parameters of the call are not known here)
+    int s_max = 0;
+    for (int a = 0; a < n_automata; ++a) s_max = std::max(s_max, (int)automata[a]->dev.S);
+    const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true, 1, s_max);
     return (int64_t)c.o_dir + words * 4 + 256;
 }
 
@@ -996,7 +1000,9 @@ extern "C" int64_t wstr_call_workspace_min_bytes(wstr_automaton *const *automata
         if (a < 0 || a >= n_automata) return WSTR_ERR_INVALID_ARGUMENT;
         widest = std::max(widest, dir_words(automata[a], lengths[r]));
     }
-    const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true);
+    int s_max = 0;
+    for (int a = 0; a < n_automata; ++a) s_max = std::max(s_max, (int)automata[a]->dev.S);
+    const CallPlan c = plan_call(n_automata, n_reads, nullptr, lengths, automata[0]->dev.mv, true, true, 1, s_max);
     return (int64_t)c.o_dir + widest * 4 + 256;
 }
 
@@ -1025,7 +1031,11 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
         return WSTR_ERR_INVALID_ARGUMENT;
     if ((out->d_seq1 || out->d_seq2) && !out->seq_off) return WSTR_ERR_INVALID_ARGUMENT;
     if (n_reads == 0) return WSTR_OK;
-    if ((params->method != 0 && params->method != 1) || params->reps_as_one != 0) return WSTR_ERR_UNSUPPORTED;
+    if (params->method != 0 && params->method != 1) return WSTR_ERR_UNSUPPORTED;
+    const int reps = params->reps_as_one != 0;
+    int s_max = 0;
+    for (int a = 0; a < n_automata; ++a)
+        if (automata[a]) s_max = std::max(s_max, (int)automata[a]->dev.S);
     if (params->states_in_segment < 2) return WSTR_ERR_INVALID_ARGUMENT;
     const int mv = automata[0]->dev.mv;
     if (params->min_values_per_state != mv) return WSTR_ERR_INVALID_ARGUMENT;
@@ -1034,7 +1044,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool own_resc = out->d_rescaled == nullptr;
     const bool own_trace = out->d_trace1 == nullptr || out->d_trace2 == nullptr;
-    const CallPlan c = plan_call(n_automata, n_reads, sig_off, lengths, mv, own_resc, own_trace);
+    const CallPlan c = plan_call(n_automata, n_reads, sig_off, lengths, mv, own_resc, own_trace, reps, s_max);
     if ((int64_t)c.o_dir >= workspace_bytes) return WSTR_ERR_WORKSPACE_TOO_SMALL;
     unsigned char *ws = static_cast<unsigned char *>(d_workspace);
     unsigned char *d_block = ws + c.o_block;
@@ -1062,7 +1072,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
         mauts[a].rep_mask = automata[a]->d_rep_mask;
         mauts[a].last_base = automata[a]->d_last_base;
         mauts[a].flank_length = automata[a]->flank_length;
-        mauts[a].pad_ = 0;
+        mauts[a].n_states = automata[a]->dev.S;
     }
     MidRead *reads = reinterpret_cast<MidRead *>(block + c.bl.o_reads);
     std::vector<int64_t> mask_off(n_reads);
@@ -1081,7 +1091,7 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
         m.pad_ = 0;
         mask_off[r] = mo;
         mo += (lengths[r] + 31) / 32;
-        so += wstr_mid_scratch_bytes(lengths[r], mv);
+        so += wstr_mid_scratch_bytes(lengths[r], mv, reps, s_max);
     }
     std::vector<Wave> waves;
     rc = plan_fill(automata, n_automata, read_automaton, sig_off, lengths, mask_off.data(), n_reads,
@@ -1124,7 +1134,11 @@ extern "C" int wstr_call_batch(wstr_automaton *const *automata, int32_t n_automa
     mp.mv = mv;
     mp.sis = params->states_in_segment;
     mp.method = params->method;
-    mp.pad_ = 0;
+    mp.reps = reps;
+    mp.s_max = s_max;
+    mp.pipe_ok = 1;
+    for (int r = 0; r < n_reads; ++r)
+        if (2 * (lengths[r] / (mv > 2 ? mv - 1 : 1) + 16) > lengths[r]) mp.pipe_ok = 0;
     mp.threshold = params->threshold;
     mp.max_std = params->max_std;
     mp.ties = out->d_ttest_ties;

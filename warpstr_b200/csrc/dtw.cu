@@ -517,7 +517,8 @@ struct alignas(16) FillSmem {
 // (7,1) and (8,1) row loops fit 128 registers (no spill in the first-pass loop, one or two local
 // loads per 3-row cycle in the masked second-pass variants), and 16 warps are 2 % faster than 12.
 // The per-lane state is (KC+KG)*(MV+1) doubles; beyond 45 of them (min_values_per_state 5 or 6) the
-// loops would spill at 128 registers, so those keep the 12-warp budget.  So does the MASKED
+// loops would spill at 128 registers, so those keep the 12-warp budget; so do the layouts with two or more
+// generic slots (their candidates' addresses and values do not fit next to nine states).  So does the MASKED
 // instantiation (second pass: rows whose mask bit is set allow the shorter dwell): its extra row
 // variants spill a few values per cycle at 128 registers, which costs what the fourth warp gains
 // (41.7 ms per pass either way).  The first-pass instantiation does not contain the masked variants
@@ -530,7 +531,7 @@ struct alignas(16) FillSmem {
 #else
 #define WSTR_FILL_BOUNDS                         \
     __launch_bounds__(32 * WSTR_WARPS_PER_CTA,   \
-                      ((KC + KG) * (MV + 1) <= 45 && !MASKED ? WSTR_K8_WARPS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
+                      ((KC + KG) * (MV + 1) <= 45 && KG <= 1 && !MASKED ? WSTR_K8_WARPS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
 #endif
 template <int KC, int KG, int DEG, int MV, bool MASKED>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
@@ -757,6 +758,7 @@ WSTR_DECL_PART(2)
 WSTR_DECL_PART(3)
 WSTR_DECL_PART(4)
 WSTR_DECL_PART(5)
+WSTR_DECL_PART(6)
 #undef WSTR_DECL_PART
 
 #if WSTR_HAS_PART(0)
@@ -771,7 +773,8 @@ int wstr_launch_fill_p0(int kc, int kg, int deg, int mv, const FillParams &p, cu
 int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
     typedef int (*part_fn)(int, int, int, int, const FillParams &, cudaStream_t);
     static const part_fn parts[] = {wstr_launch_fill_p0, wstr_launch_fill_p1, wstr_launch_fill_p2,
-                                    wstr_launch_fill_p3, wstr_launch_fill_p4, wstr_launch_fill_p5};
+                                    wstr_launch_fill_p3, wstr_launch_fill_p4, wstr_launch_fill_p5,
+                                    wstr_launch_fill_p6};
     for (part_fn f : parts) {
         const int rc = f(kc, kg, deg, mv, p, s);
         if (rc != WSTR_ERR_UNSUPPORTED) return rc;
@@ -814,6 +817,15 @@ int wstr_launch_fill_p4(int kc, int kg, int deg, int mv, const FillParams &p, cu
 int wstr_launch_fill_p5(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
     WSTR_CASE(6, 4, 5)
     WSTR_CASE(6, 4, 6)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+// nine and eleven states per lane: DM2 / RFC1 (265-267 states) and the 324-state strand of (CAN) without
+// the padding of the (8,2) and (8,4) splits
+#if WSTR_HAS_PART(6)
+int wstr_launch_fill_p6(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(7, 2, 4)
+    WSTR_CASE(7, 4, 4)
     return WSTR_ERR_UNSUPPORTED;
 }
 #endif

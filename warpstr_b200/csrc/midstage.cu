@@ -363,13 +363,54 @@ __device__ double run_median(const double *xs, int n) {
     return (n & 1) ? v_hi : (v_lo + v_hi) / 2.0;
 }
 
+// k-th smallest (0-based) of xs[0..n) without a copy: most-significant-bit-first selection on the
+// order-preserving integer image of the doubles, 64 counting passes (for the long lists of
+// reps_as_one, where a state's samples come from every visit of it)
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ double select_kth(const double *xs, int n, int k) {
+    unsigned long long prefix = 0ull;
+    for (int bit = 63; bit >= 0; --bit) {
+        const unsigned long long above = bit == 63 ? 0ull : ~((2ull << bit) - 1ull);   // bits already decided
+        int zeros = 0;
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long key = order_key(xs[i]);
+            zeros += ((key & above) == prefix && !((key >> bit) & 1ull)) ? 1 : 0;
+        }
+        if (k >= zeros) {
+            k -= zeros;
+            prefix |= 1ull << bit;
+        }
+    }
+    const unsigned long long b = (prefix >> 63) ? (prefix & 0x7fffffffffffffffull) : ~prefix;
+    return __longlong_as_double(static_cast<long long>(b));
+}
+__device__ double list_median(const double *xs, int n) {
+    if (n <= 48) return run_median(xs, n);
+    if (n & 1) return select_kth(xs, n, n / 2);
+    return (select_kth(xs, n, n / 2 - 1) + select_kth(xs, n, n / 2)) / 2.0;
+}
+
 struct Scratch {
     int32_t *run_start, *run_state;
     double *sv, *px, *py, *sx, *sy;
-    int32_t *sidx;       // sort scratch for long reads
+    int32_t *sidx;       // sort scratch for long reads; reps_as_one: where each run's samples go in gvals
+    int32_t *astate;     // reps_as_one: state of each alignment entry
+    int32_t *cnt, *base; // reps_as_one: samples per state, first slot of each state in gvals ([S], [S+1])
+    double *gvals;       // reps_as_one: the read's samples grouped by state, time order inside a state ([T])
 };
 
-__device__ __forceinline__ Scratch carve(unsigned char *ws, int R) {
+__host__ __device__ inline size_t scratch_core_bytes(int R) {
+    size_t b = ((8 * (size_t)R + 4 + 7) / 8) * 8;   // run_start (R+1) + run_state (R), int32
+    b += 5 * 8 * (size_t)R;                         // sv, px, py, sx, sy
+    b += 4 * (size_t)R;                             // sidx
+    b += 4 * (size_t)R;                             // astate
+    return (b + 7) / 8 * 8;
+}
+
+__device__ __forceinline__ Scratch carve(unsigned char *ws, int R, int T, int s_max) {
     Scratch s;
     s.run_start = reinterpret_cast<int32_t *>(ws);   // R+1
     s.run_state = s.run_start + (R + 1);             // R
@@ -379,6 +420,11 @@ __device__ __forceinline__ Scratch carve(unsigned char *ws, int R) {
     s.sx = s.py + R;
     s.sy = s.sx + R;
     s.sidx = reinterpret_cast<int32_t *>(s.sy + R);
+    s.astate = s.sidx + R;
+    unsigned char *ext = ws + scratch_core_bytes(R);          // only there when the call has reps_as_one
+    s.gvals = reinterpret_cast<double *>(ext);
+    s.cnt = reinterpret_cast<int32_t *>(s.gvals + T);
+    s.base = s.cnt + s_max;
     return s;
 }
 
@@ -387,6 +433,17 @@ __device__ __forceinline__ Scratch carve(unsigned char *ws, int R) {
 // the others are butterflies), so the positions m..P-1 can be left out as virtual +inf.  Ties
 // are broken by idx, which makes the order the stable one np.argsort(kind='stable') /
 // sorted() produce.  key/idx may live in shared or global memory.
+__device__ __forceinline__ void sort_cx(double *key, int32_t *idx, int i, int l) {
+    const double ka = key[i], kb = key[l];
+    const int32_t ia = idx[i], ib = idx[l];
+    if (kb < ka || (kb == ka && ib < ia)) {
+        key[i] = kb;
+        key[l] = ka;
+        idx[i] = ib;
+        idx[l] = ia;
+    }
+}
+
 __device__ void warp_sort_pairs(double *key, int32_t *idx, int m, int lane) {
     int P = 1;
     while (P < m) P <<= 1;
@@ -397,16 +454,52 @@ __device__ void warp_sort_pairs(double *key, int32_t *idx, int m, int lane) {
                 // t-th pair of this step: i has bit j clear
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int l = i ^ flip;
-                if (l < m) {                                    // i < l always; beyond m: +inf, nothing to do
-                    const double ka = key[i], kb = key[l];
-                    const int32_t ia = idx[i], ib = idx[l];
-                    if (kb < ka || (kb == ka && ib < ia)) {
-                        key[i] = kb;
-                        key[l] = ka;
-                        idx[i] = ib;
-                        idx[l] = ia;
-                    }
+                if (l < m) sort_cx(key, idx, i, l);             // i < l always; beyond m: +inf, nothing to do
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// The same network for lists too long for shared memory (a thousand-repeat read has ~6 000 pairs): the
+// steps whose partners are at least CH apart run on the global arrays, every run of steps with closer
+// partners is done chunk by chunk in shared memory (one load and one store of the chunk for up to
+// log2(CH) steps) -- 10 global passes instead of 91 for 8 192 positions.
+template <int CH>
+__device__ void warp_sort_pairs_tiled(double *gkey, int32_t *gidx, int m, int lane, double *skey, int32_t *sidx) {
+    int P = 1;
+    while (P < m) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= CH; j >>= 1) {                            // partners in different chunks
+            const int flip = j == (k >> 1) ? k - 1 : j;
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i ^ flip;
+                if (l < m) sort_cx(gkey, gidx, i, l);
+            }
+            __syncwarp();
+        }
+        if (j == 0) continue;
+        for (int c0 = 0; c0 < m; c0 += CH) {                  // partners inside one CH-aligned chunk
+            const int n = min(CH, m - c0);
+            for (int e = lane; e < n; e += 32) {
+                skey[e] = gkey[c0 + e];
+                sidx[e] = gidx[c0 + e];
+            }
+            __syncwarp();
+            for (int jj = j; jj > 0; jj >>= 1) {
+                const int flip = jj == (k >> 1) ? k - 1 : jj;   // (k <= CH: the mirror step is inside the chunk)
+                for (int t = lane; t < (CH >> 1); t += 32) {
+                    const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    const int l = i ^ flip;
+                    if (l < n) sort_cx(skey, sidx, i, l);
                 }
+                __syncwarp();
+            }
+            for (int e = lane; e < n; e += 32) {
+                gkey[c0 + e] = skey[e];
+                gidx[c0 + e] = sidx[e];
             }
             __syncwarp();
         }
@@ -432,7 +525,7 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
         const double *x = p.x + rd.sig_off;
         const int32_t *trace = p.trace + rd.sig_off;
         const int R = rd.run_cap;
-        const Scratch sc = carve(p.scratch + rd.ws_off, R);
+        const Scratch sc = carve(p.scratch + rd.ws_off, R, T, p.s_max);
         int32_t *run_start = sc.run_start, *run_state = sc.run_state;
         int fail = 0;
 
@@ -474,9 +567,11 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
         if (!fail && lane == 0) run_start[n_runs] = T;
         __syncwarp();
 
-        // ---- per-run statistics (caller.py:65-96, 23-39) ---------------------------------------
-        int m = 0;   // good pairs
-        if (!fail) {
+        // ---- alignment list (caller.py:65-96) and its usable pairs (:23-39) -----------------------
+        int m = 0;         // good pairs
+        int n_align = 0;   // entries of the alignment list
+        if (!fail && !p.reps) {
+            n_align = n_runs;
             for (int r0 = 0; r0 < n_runs; r0 += 32) {
                 const int r = r0 + lane;
                 bool g = false;
@@ -512,6 +607,76 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
             __syncwarp();
             if (m <= 3) fail = WSTR_READ_SPLINE;   // splrep: 'm > k must hold'
         }
+        if (!fail && p.reps) {
+            // rescaling.reps_as_one (caller.py:69-79): one entry per distinct state of the path, ascending
+            // state index (np.unique), over ALL samples mapped to the state in time order
+            // (np.take(signal, np.where(trace == state)))
+            const int S = A.n_states;
+            int32_t *cnt = sc.cnt, *base = sc.base, *dest = sc.sidx;
+            for (int j = lane; j < S; j += 32) cnt[j] = 0;
+            __syncwarp();
+            for (int r = lane; r < n_runs; r += 32) atomicAdd(&cnt[run_state[r]], run_start[r + 1] - run_start[r]);
+            __syncwarp();
+            if (lane == 0) {
+                int acc = 0;
+                for (int j = 0; j < S; ++j) {
+                    base[j] = acc;
+                    acc += cnt[j];
+                }
+                base[S] = acc;
+                // every run's place inside its state's group: runs in time order, one after the other
+                for (int j = 0; j < S; ++j) cnt[j] = base[j];
+                for (int r = 0; r < n_runs; ++r) {
+                    const int st = run_state[r];
+                    dest[r] = cnt[st];
+                    cnt[st] += run_start[r + 1] - run_start[r];
+                }
+            }
+            __syncwarp();
+            for (int r = lane; r < n_runs; r += 32) {
+                const int a = run_start[r], n = run_start[r + 1] - a, d = dest[r];
+                for (int k = 0; k < n; ++k) sc.gvals[d + k] = x[a + k];
+            }
+            __syncwarp();
+            for (int j0 = 0; j0 < S; j0 += 32) {
+                const int j = j0 + lane;
+                const int n = j < S ? base[j + 1] - base[j] : 0;
+                bool g = false;
+                double value = 0.0, expect = 0.0;
+                if (n > 0) {
+                    const double *xs = sc.gvals + base[j];
+                    const double avg = pairwise_sum([xs](int i) { return xs[i]; }, 0, n) / (double)n;
+                    value = p.method == 1 ? list_median(xs, n) : avg;
+                    expect = A.values[j];
+                    if (n >= p.mv) {
+                        const double ss = pairwise_sum(
+                            [xs, avg](int i) {
+                                const double d = xs[i] - avg;
+                                return d * d;
+                            },
+                            0, n);
+                        const double sd = sqrt(ss / (double)n);
+                        g = sd < p.max_std && fabs(expect - value) <= p.threshold;
+                    }
+                }
+                const unsigned present = __ballot_sync(FULL, n > 0);
+                if (n > 0) {
+                    const int k = n_align + __popc(present & ((1u << lane) - 1u));
+                    sc.sv[k] = value;
+                    sc.astate[k] = j;
+                }
+                n_align += __popc(present);
+                const unsigned bal = __ballot_sync(FULL, g);
+                if (g) {
+                    const int k = m + __popc(bal & ((1u << lane) - 1u));
+                    sc.px[k] = value;
+                    sc.py[k] = expect;
+                }
+                m += __popc(bal);
+            }
+            __syncwarp();
+            if (m <= 3) fail = WSTR_READ_SPLINE;
+        }
 
         if (!SECOND && !fail) {
             // ---- stable sort by state value (caller.py:306) -----------------------------------------
@@ -525,7 +690,8 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
                 idx[i] = i;
             }
             __syncwarp();
-            warp_sort_pairs(key, idx, m, lane);
+            if (in_smem) warp_sort_pairs(key, idx, m, lane);
+            else warp_sort_pairs_tiled<SORT_SMEM>(key, idx, m, lane, s_key[threadIdx.x >> 5], s_idx[threadIdx.x >> 5]);
             for (int i = lane; i < m; i += 32) {
                 sc.sx[i] = key[i];
                 sc.sy[i] = sc.py[idx[i]];
@@ -594,6 +760,8 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
             st.end = end;
             st.ra = ra;
             st.nb = nb;
+            st.n_align = n_align;
+            st.pad_ = 0;
             p.state[q] = st;
             if (fail) p.status[rd.read] = fail;
         }
@@ -601,15 +769,16 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
     }
 }
 
-// Kernel B (one thread per read, first pass only): the smoothing spline's accepted first
-// iteration.  Strictly sequential per read, so reads are spread over threads.
+// Kernel B (first pass only): the smoothing spline's accepted first iteration, one thread per read.
+// Strictly sequential per read (4 m dependent Givens rotations), so reads are spread over threads: the
+// form for large batches, where a hundred thousand reads keep every lane busy.
 __global__ void __launch_bounds__(128) mid_fit_kernel(const MidParams p) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= p.n) return;
     const MidRead rd = p.reads[q];
     if (p.status[rd.read] != WSTR_READ_OK) return;
     const MidState st = p.state[q];
-    const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap);
+    const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap, rd.T, p.s_max);
     Cubic cu;
     lsq_cubic(sc.sx, sc.sy, st.m, cu);
     const double s = (double)st.m, acc = 0.001 * s;
@@ -624,6 +793,171 @@ __global__ void __launch_bounds__(128) mid_fit_kernel(const MidParams p) {
     o[4] = cu.c[2];
     o[5] = cu.c[3];
     o[6] = cu.fp;
+}
+
+// Kernel B for small batches of long reads (a few thousand reads of thousands of pairs each: the sweep's
+// latency is then all there is).  The Givens sweep is sequential per matrix element (row `it` rotates
+// into the triangle left by rows 0..it-1), but its four columns form a pipeline: while row `it` is
+// rotated into column i, row `it-1` can be rotated into column i+1.  Four lanes work on one read, each
+// owning one column of the triangle (pivot, off-diagonals, right-hand side) and handing the rest of the
+// rotated row to the next lane by shuffle; eight reads share a warp.  A lane always sees its pivot as
+// the first element of what it receives and passes on what is right of it, so all lanes run the same
+// instructions (a column with fewer off-diagonals rotates zeros).  The rows' B-spline bases (fpbspl) do
+// not depend on one another: the warp evaluates them for all rows first, 32 at a time, into the read's
+// free scratch (the unsorted-pair arrays and the not yet written rescaled signal).  Every matrix
+// element sees the same rotations in the same order as in FITPACK's loop: the coefficients are bit-equal
+// to the thread-per-read kernel's and to scipy's.  A read costs m + 3 pipeline steps instead of 4 m
+// dependent rotations.
+constexpr int FIT_STAGES = 4;
+constexpr int FIT_READS_PER_WARP = 32 / FIT_STAGES;   // 8
+constexpr int FIT_PIPE_MAX_READS = 16384;             // larger batches fill the GPU with one thread per read
+
+__device__ __forceinline__ double shfl_up_d(double v, int delta) { return __shfl_up_sync(FULL, v, delta); }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+__global__ void __launch_bounds__(128) mid_fit_pipe_kernel(const MidParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slot = lane / FIT_STAGES, stage = lane - slot * FIT_STAGES;
+
+    // ---- the basis of every row of the warp's reads, all lanes on one read at a time ----------------
+    for (int g = 0; g < FIT_READS_PER_WARP; ++g) {
+        const int qg = warp * FIT_READS_PER_WARP + g;
+        if (qg >= p.n) break;
+        const MidRead rd = p.reads[qg];
+        if (p.status[rd.read] != WSTR_READ_OK) continue;
+        const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap, rd.T, p.s_max);
+        const int mg = p.state[qg].m;
+        const double xb = sc.sx[0], xe = sc.sx[mg - 1];
+        const Divisor span = make_divisor(xe - xb);
+        double *b2 = p.rescaled + rd.sig_off, *b3 = b2 + rd.run_cap;     // 2 * run_cap <= T, checked by the launcher
+        for (int it = lane; it < mg; it += 32) {
+            double h[4];
+            bspl3<true>(xb, xe, span, sc.sx[it], h);
+            sc.px[it] = h[0];
+            sc.py[it] = h[1];
+            b2[it] = h[2];
+            b3[it] = h[3];
+        }
+    }
+    __syncwarp();
+
+    const int q = warp * FIT_READS_PER_WARP + slot;
+    const bool active = q < p.n && p.status[p.reads[q < p.n ? q : 0].read] == WSTR_READ_OK;
+    int m = 0;
+    const double *sy = nullptr, *b0 = nullptr, *b1 = nullptr, *b2 = nullptr, *b3 = nullptr;
+    double xb = 0.0, xe = 0.0;
+    if (active) {
+        const MidRead rd = p.reads[q];
+        const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap, rd.T, p.s_max);
+        m = p.state[q].m;
+        sy = sc.sy;
+        b0 = sc.px;
+        b1 = sc.py;
+        b2 = p.rescaled + rd.sig_off;
+        b3 = b2 + rd.run_cap;
+        xb = sc.sx[0];
+        xe = sc.sx[m - 1];
+    }
+    int steps = m + FIT_STAGES - 1;
+    for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+
+    // this lane's column of the triangle (stage = column): a0 the pivot, a1..a3 the row's tail
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, z = 0.0, fp = 0.0;
+    // what this lane hands to the next stage: the row right of this stage's column, after its rotation
+    double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0, oy = 0.0;
+    int ovalid = 0;
+    // the first column reads its rows from memory, one step ahead of their use
+    const bool feeds = active && stage == 0;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0, ny = 0.0;
+    if (feeds && m > 0) {
+        n0 = b0[0];
+        n1 = b1[0];
+        n2 = b2[0];
+        n3 = b3[0];
+        ny = sy[0];
+    }
+
+    for (int tau = 0; tau < steps; ++tau) {
+        // the previous stage's output of the step before
+        double t0 = shfl_up_d(o0, 1), t1 = shfl_up_d(o1, 1), t2 = shfl_up_d(o2, 1), t3 = shfl_up_d(o3, 1);
+        double yi = shfl_up_d(oy, 1);
+        int valid = __shfl_up_sync(FULL, ovalid, 1);
+        if (stage == 0) {
+            t0 = n0;
+            t1 = n1;
+            t2 = n2;
+            t3 = n3;
+            yi = ny;
+            valid = feeds && tau < m;
+            if (feeds && tau + 1 < m) {
+                n0 = b0[tau + 1];
+                n1 = b1[tau + 1];
+                n2 = b2[tau + 1];
+                n3 = b3[tau + 1];
+                ny = sy[tau + 1];
+            }
+        }
+        ovalid = active && valid;
+        if (ovalid) {
+            if (t0 != 0.0) {                       // fpcurf skips a zero pivot
+                double c, sn;
+                givens(t0, a0, c, sn);
+                rotate(c, sn, yi, z);
+                rotate(c, sn, t1, a1);
+                rotate(c, sn, t2, a2);
+                rotate(c, sn, t3, a3);
+            }
+            fp = fp + yi * yi;                     // (the last column's is the residual sum)
+            o0 = t1;
+            o1 = t2;
+            o2 = t3;
+            o3 = 0.0;
+            oy = yi;
+        }
+    }
+
+    // fpback (n = 4, bandwidth 4) on the first lane of the read; the other columns come over by shuffle
+    const int l0 = slot * FIT_STAGES;
+    const double A00 = shfl_d(a0, l0), A01 = shfl_d(a1, l0), A02 = shfl_d(a2, l0), A03 = shfl_d(a3, l0), Z0 = shfl_d(z, l0);
+    const double A10 = shfl_d(a0, l0 + 1), A11 = shfl_d(a1, l0 + 1), A12 = shfl_d(a2, l0 + 1), Z1 = shfl_d(z, l0 + 1);
+    const double A20 = shfl_d(a0, l0 + 2), A21 = shfl_d(a1, l0 + 2), Z2 = shfl_d(z, l0 + 2);
+    const double A30 = shfl_d(a0, l0 + 3), Z3 = shfl_d(z, l0 + 3), FP = shfl_d(fp, l0 + 3);
+    if (active && stage == 0) {
+        double c[4];
+        c[3] = Z3 / A30;
+        {   // i = 2: store = z[2] - c[3]*a[2][1]
+            double store = Z2;
+            store = store - c[3] * A21;
+            c[2] = store / A20;
+        }
+        {   // i = 1: store = z[1] - c[2]*a[1][1] - c[3]*a[1][2]
+            double store = Z1;
+            store = store - c[2] * A11;
+            store = store - c[3] * A12;
+            c[1] = store / A10;
+        }
+        {   // i = 0: store = z[0] - c[1]*a[0][1] - c[2]*a[0][2] - c[3]*a[0][3]
+            double store = Z0;
+            store = store - c[1] * A01;
+            store = store - c[2] * A02;
+            store = store - c[3] * A03;
+            c[0] = store / A00;
+        }
+        const MidRead rd = p.reads[q];
+        const double s = (double)m, acc = 0.001 * s;
+        const double fpms = FP - s;
+        // fpcurf: accept if |fp-s| < acc or fp < s; otherwise knots would be added
+        if ((!(fabs(fpms) < acc) && !(fpms < 0.0)) || !(FP == FP)) p.status[rd.read] = WSTR_READ_SPLINE_KNOTS;
+        double *o = p.cubic + (size_t)q * 8;
+        o[0] = xb;
+        o[1] = xe;
+        o[2] = c[0];
+        o[3] = c[1];
+        o[4] = c[2];
+        o[5] = c[3];
+        o[6] = FP;
+    }
 }
 
 // Kernel C (one warp per read): rescaled signal + bad-repeat mask (first pass), cost, sequence.
@@ -641,7 +975,7 @@ __global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
         const MidState st = p.state[q];
         const int T = rd.T;
         const double *x = p.x + rd.sig_off;
-        const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap);
+        const Scratch sc = carve(p.scratch + rd.ws_off, rd.run_cap, rd.T, p.s_max);
         const int32_t *run_start = sc.run_start, *run_state = sc.run_state;
         const int n_runs = st.n_runs, ra = st.ra, nb = st.nb;
         int fail = 0;
@@ -714,11 +1048,14 @@ __global__ void __launch_bounds__(128) mid_finish_kernel(const MidParams p) {
 
         // ---- state-wise cost (caller.py:138-139) and decoded sequence (:178-187) ----------------
         {
+            // alignment[start:end] (start, end are run indices even when the list is per state: the
+            // reference applies them as they are, caller.py:138-139)
             const int start = st.start;
-            const int e_clip = min(st.end, n_runs);
+            const int e_clip = min(st.end, st.n_align);
             const int cnt = e_clip > start ? e_clip - start : 0;
+            const int32_t *a_state = p.reps ? sc.astate : run_state;
             for (int r = start + lane; r < start + cnt; r += 32)
-                sc.px[r - start] = fabs(sc.sv[r] - A.values[run_state[r]]);
+                sc.px[r - start] = fabs(sc.sv[r] - A.values[a_state[r]]);
             __syncwarp();
             if (lane == 0) {
                 double cost;
@@ -770,17 +1107,19 @@ int wstr_launch_midstage(const MidParams &p, bool second, cudaStream_t s) {
         mid_finish_kernel<true><<<grid, 128, 0, s>>>(p);
     } else {
         mid_stats_kernel<false><<<grid, 128, 0, s>>>(p);
-        mid_fit_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
+        if (p.n <= FIT_PIPE_MAX_READS && p.pipe_ok)
+            mid_fit_pipe_kernel<<<(p.n + 4 * FIT_READS_PER_WARP - 1) / (4 * FIT_READS_PER_WARP), 128, 0, s>>>(p);
+        else
+            mid_fit_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
         mid_finish_kernel<false><<<grid, 128, 0, s>>>(p);
     }
     WSTR_CUDA(cudaGetLastError());
     return WSTR_OK;
 }
 
-int64_t wstr_mid_scratch_bytes(int T, int mv) {
+int64_t wstr_mid_scratch_bytes(int T, int mv, int reps, int s_max) {
     const int64_t R = T / (mv > 2 ? mv - 1 : 1) + 16;
-    int64_t b = ((8 * R + 4 + 7) / 8) * 8;   // run_start (R+1) + run_state (R), int32
-    b += 5 * 8 * R;                           // sv, px, py, sx, sy
-    b += 4 * R;                               // sidx
+    int64_t b = (int64_t)scratch_core_bytes((int)R);
+    if (reps) b += 8 * (int64_t)T + 4 * (2 * (int64_t)s_max + 2);   // gvals, cnt, base
     return (b + 255) / 256 * 256;
 }

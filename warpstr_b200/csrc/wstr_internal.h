@@ -85,7 +85,7 @@ struct MidAutomaton {
     const uint8_t *rep_mask;     // [S]
     const uint8_t *last_base;    // [S]
     int32_t flank_length;
-    int32_t pad_;
+    int32_t n_states;
 };
 
 struct MidRead {
@@ -100,6 +100,7 @@ struct MidRead {
 
 struct MidState {
     int32_t n_runs, m, start, end, ra, nb;
+    int32_t n_align, pad_;       // entries of the alignment list: runs, or distinct states with reps_as_one
 };
 
 struct MidParams {
@@ -119,14 +120,16 @@ struct MidParams {
     uint8_t *seq;                // may be NULL
     int32_t *status;
     int32_t mv, sis;
-    int32_t method, pad_;        // 0 mean, 1 median (state value of a run)
+    int32_t method, reps;        // 0 mean, 1 median (state value of a run); reps: rescaling.reps_as_one
+    int32_t s_max, pipe_ok;      // most states of any automaton of the call (sizes the reps_as_one scratch);
+                                 // pipe_ok: every read has 2 * run_cap <= T (the pipelined fit parks its basis there)
     double threshold, max_std;
     int32_t *ties;               // may be NULL: t-test decisions within tie_ulps of flipping, per read (first pass)
     long long tie_ulps;
 };
 
 int wstr_launch_midstage(const MidParams &p, bool second, cudaStream_t s);
-int64_t wstr_mid_scratch_bytes(int T, int mv);
+int64_t wstr_mid_scratch_bytes(int T, int mv, int reps, int s_max);
 
 struct wstr_automaton {
     DevAutomaton dev;            // pointers into d_blob
