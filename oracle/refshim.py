@@ -3,7 +3,7 @@ so that its own functions can be used to pin the oracle, to generate golden vect
 (tests/golden/, see oracle/make_golden.py) and as the timed CPU arm of bench.py.
 In this container the modules come from /root/reference; on the GPU box, where that
 tree does not exist, from oracle/_ref/ -- the same modules byte-compiled by
-oracle/build_ref.py (source-less .pyc, git-ignored, shipped like a built .so).
+oracle/build_ref.py (source-less bytecode, git-ignored, shipped like a built .so).
 
 The reference parses argv and its YAML config at import time
 (src/config.py:174-210), needs h5py / pysam / Biopython / matplotlib / seaborn
@@ -55,7 +55,15 @@ def source_available() -> bool:
 
 
 def compiled_available() -> bool:
-    return os.path.exists(os.path.join(COMPILED_ROOT, 'src', 'caller', 'wrapper.pyc'))
+    return os.path.exists(os.path.join(COMPILED_ROOT, 'src', 'caller', 'wrapper.refbc'))
+
+
+def _compiled_hook(path):
+    """sys.path hook: directories under oracle/_ref hold modules as source-less bytecode, suffix .refbc."""
+    from importlib.machinery import FileFinder, SourcelessFileLoader
+    if not os.path.abspath(path).startswith(COMPILED_ROOT):
+        raise ImportError
+    return FileFinder(path, (SourcelessFileLoader, ['.refbc']))
 
 
 def _stub(name, **kw):
@@ -99,6 +107,9 @@ def load():
         import yaml
         from warpstr_b200 import config as our_config
         root, cwd = COMPILED_ROOT, tmp
+        if _compiled_hook not in sys.path_hooks:
+            sys.path_hooks.insert(0, _compiled_hook)
+            sys.path_importer_cache.clear()
         os.makedirs(os.path.join(tmp, 'src'), exist_ok=True)
         with open(os.path.join(tmp, 'src', 'default.yaml'), 'w') as fh:
             yaml.safe_dump(our_config.DEFAULTS, fh)
