@@ -186,6 +186,7 @@ constexpr int PER = 8;               // samples per thread per tile
 constexpr int TILE = NT * PER;       // 2048
 constexpr int HBINS = 8192;          // shared histogram covers values [0, HBINS)
 constexpr int GBINS = 65536;         // global fallback histogram covers every int16
+constexpr int SPIKE_CAP = 256;       // out-of-range samples of one read the barrier-free path can hold
 
 struct NormParams {
     const int16_t *raw;
@@ -205,7 +206,12 @@ struct NormSmem {
     // tile[HALO + t] = sample t of the current tile; tile[HALO-2], tile[HALO-1] = the two
     // (patched) samples before it.  HALO = 8 keeps the tile 16-byte aligned for vector access.
     alignas(16) int16_t tile[TILE + 16];
-    uint32_t spike_bits[TILE / 32];  // Brute: out-of-range samples of the current tile (all zero between tiles)
+    uint32_t spike_bits[TILE / 32];  // Brute, tile path: out-of-range samples of the current tile (all zero between tiles)
+    // Brute, barrier-free path: the out-of-range samples of the read, (index << 32 | slot) for sorting, and
+    // the raw samples i-2 .. i+2 around each, fetched by the thread that found it
+    unsigned long long spike_key[SPIKE_CAP];
+    int16_t spike_w[SPIKE_CAP][5];
+    int32_t n_spikes;
     int32_t next_read;
     int32_t vmin, vmax;
     int32_t ghist_dirty;
@@ -290,12 +296,57 @@ __device__ double absdev_at_rank(const NormSmem &sm, const uint32_t *gh, double 
     return 0.0;
 }
 
-// One CTA per read, one pass over the samples in tiles of 2048.  The read is walked from the
+// ---- order statistics off the prefix-summed histogram (no sample outside [0, HBINS)) ------------------
+// After the scan the CTA turns hist[vmin..vmax] into inclusive prefix sums in place; every rank query is
+// then a binary search by one thread instead of a walk over the bins by a warp.
+__device__ __forceinline__ int64_t cum_le(const NormSmem &sm, int v) {     // samples <= v
+    if (v < sm.vmin) return 0;
+    if (v >= sm.vmax) return sm.hist[sm.vmax];
+    return sm.hist[v];
+}
+__device__ int value_at_rank_cum(const NormSmem &sm, int64_t rank) {       // smallest v with cum(v) > rank
+    int a = sm.vmin, b = sm.vmax;
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (cum_le(sm, mid) > rank) b = mid;
+        else a = mid + 1;
+    }
+    return a;
+}
+__device__ double absdev_at_rank_cum(const NormSmem &sm, double shift, int64_t rank) {
+    // values by |v - shift|: the pairs (fl - m, fl + 1 + m), m = 0, 1, ...; the first m pairs hold the
+    // samples in [fl - m + 1, fl + m]
+    const int fl = (int)floor(shift);
+    const int span = max(fl - sm.vmin, sm.vmax - (fl + 1)) + 1;
+    int a = 0, b = span;                                                   // smallest m with count(m + 1) > rank
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (cum_le(sm, fl + mid + 1) - cum_le(sm, fl - mid - 1) > rank) b = mid;
+        else a = mid + 1;
+    }
+    const int mm = a;
+    const int64_t before = cum_le(sm, fl + mm) - cum_le(sm, fl - mm);
+    const int64_t scl = cum_le(sm, fl - mm) - cum_le(sm, fl - mm - 1);
+    const int64_t sch = cum_le(sm, fl + 1 + mm) - cum_le(sm, fl + mm);
+    const double dl = fabs((double)(fl - mm) - shift), du = fabs((double)(fl + 1 + mm) - shift);
+    const int64_t within = rank - before;
+    if (dl <= du) return within < scl ? dl : du;                           // inside the pair the nearer value first
+    return within < sch ? du : dl;
+}
+
+// One CTA per read, one pass over the samples, 2048 per step.  The read is walked from the
 // 16-byte boundary at or before its first sample, so every thread loads its 8 samples with one
-// aligned 16-byte load, a tile ahead of their use (samples in front of / behind the read are
-// masked).  Per tile there is a single barrier unless the tile holds an out-of-range sample
-// (Brute: two more, and only the threads that hold such a sample and one patching lane do any
-// work) or a median filter is on.  Indices inside a read are 32-bit.
+// aligned 16-byte load, a step ahead of their use (samples in front of / behind the read are
+// masked).  Indices inside a read are 32-bit.
+//
+// Brute / None (the reference's default and its off switch) take a loop without a barrier: a
+// histogram is additive, so every thread counts its RAW samples unconditionally and only notes
+// where the out-of-range ones are; afterwards one lane walks those (sorted, typically a few tens
+// per read) in ascending order exactly like fast5.py:90-101 -- later medians see earlier fixes --
+// moves each patched sample from its old histogram bin to its new one and fixes it in the stashed
+// window.  A read with more than SPIKE_CAP such samples, and the median-filter modes (every sample
+// changes), take the tile loop: the tile in shared memory, one barrier per tile, the patching
+// done tile by tile.
 __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const NormParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NormSmem &sm = *reinterpret_cast<NormSmem *>(smem_raw);
@@ -320,6 +371,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             sm.vmin = 32767;
             sm.vmax = -32768;
             sm.ghist_dirty = 0;
+            sm.n_spikes = 0;
         }
         if (tid < HALO) sm.tile[tid] = 0;
         if (tid < TILE / 32) sm.spike_bits[tid] = 0u;
@@ -334,8 +386,101 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             const int v = k * NT + tid;
             return v < n_vec ? __ldg(vec + v) : make_uint4(0u, 0u, 0u, 0u);
         };
-        uint4 nxt = fetch(0);
         int lmin = 32767, lmax = -32768;
+        // ---- barrier-free scan (Brute / None) -----------------------------------------------------
+        auto scan_fast = [&]() {
+            uint4 nxt = fetch(0), nxt2 = fetch(1);                 // two steps of loads in flight per thread
+            for (int k = 0; k < n_tiles; ++k) {
+                union {
+                    uint4 q;
+                    int16_t h[PER];
+                } cur;
+                cur.q = nxt;
+                nxt = nxt2;
+                nxt2 = fetch(k + 2);
+                const int t_base = k * TILE - mis;
+                const int g0 = t_base + tid * PER;
+                const bool interior = t_base >= 0 && t_base + TILE <= N;
+                const bool in_window = t_base <= hi && t_base + TILE > lo;
+                int tmin, tmax;
+                if (interior) {
+                    const unsigned mn = __vmins2(__vmins2(cur.q.x, cur.q.y), __vmins2(cur.q.z, cur.q.w));
+                    const unsigned mx = __vmaxs2(__vmaxs2(cur.q.x, cur.q.y), __vmaxs2(cur.q.z, cur.q.w));
+                    tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
+                    tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
+                } else {
+                    tmin = 32767;
+                    tmax = -32768;
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int g = g0 + u;
+                        if (g >= 0 && g < N) {
+                            tmin = min(tmin, (int)cur.h[u]);
+                            tmax = max(tmax, (int)cur.h[u]);
+                        }
+                    }
+                }
+                if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {       // note where Brute will patch
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int g = g0 + u;
+                        if (g >= 0 && g < N && (cur.h[u] > 1000 || cur.h[u] < 250)) {
+                            const int pos = atomicAdd(&sm.n_spikes, 1);
+                            if (pos < SPIKE_CAP) {
+                                sm.spike_key[pos] = ((unsigned long long)(unsigned)g << 32) | (unsigned)pos;
+#pragma unroll
+                                for (int d = 0; d < 5; ++d) {
+                                    const int idx = g - 2 + d;
+                                    sm.spike_w[pos][d] = (idx >= 0 && idx < N) ? raw[idx] : (int16_t)0;
+                                }
+                            }
+                        }
+                    }
+                }
+                lmin = min(lmin, tmin);
+                lmax = max(lmax, tmax);
+                if (interior && tmin >= 0 && tmax < HBINS) {
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) atomicAdd(&sm.hist[cur.h[u]], 1u);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int g = g0 + u;
+                        if (g < 0 || g >= N) continue;
+                        const int vv = cur.h[u];
+                        if (vv >= 0 && vv < HBINS) {
+                            atomicAdd(&sm.hist[vv], 1u);
+                        } else {
+                            atomicAdd(&gh[vv + 32768], 1u);
+                            sm.ghist_dirty = 1;
+                        }
+                    }
+                }
+                if (in_window) {
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int g = g0 + u;
+                        if (g >= lo && g <= hi && g < N) stash[g - lo] = cur.h[u];
+                    }
+                }
+            }
+        };
+        // one lane: move a sample between histogram bins
+        auto hist_move = [&](int from, int to) {
+            if (from >= 0 && from < HBINS) sm.hist[from] -= 1u;
+            else {
+                gh[from + 32768] -= 1u;
+                sm.ghist_dirty = 1;
+            }
+            if (to >= 0 && to < HBINS) sm.hist[to] += 1u;
+            else {
+                gh[to + 32768] += 1u;
+                sm.ghist_dirty = 1;
+            }
+        };
+        // ---- tile scan (median filters; Brute with very many out-of-range samples) -----------------------
+        auto scan_tiles = [&]() {
+        uint4 nxt = fetch(0);
         for (int k = 0; k < n_tiles; ++k) {
             union {
                 uint4 q;
@@ -488,29 +633,145 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             // the next iteration's tile store cannot pass this tile's readers: in the slow paths they
             // are fenced by the barriers above, in the fast path nobody reads the tile
         }
+        };
+
+        if (p.spike_mode <= 1) {
+            scan_fast();
+            __syncthreads();
+            const int ns = sm.n_spikes;
+            if (ns > SPIKE_CAP) {
+                // too many for the list: start over on the tile path
+                __syncthreads();
+                for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
+                if (sm.ghist_dirty)
+                    for (int b = tid; b < GBINS; b += NT) gh[b] = 0u;
+                lmin = 32767;
+                lmax = -32768;
+                __syncthreads();
+                if (tid == 0) sm.ghist_dirty = 0;
+                __syncthreads();
+                scan_tiles();
+            } else if (ns > 0 && warp == 0) {
+                // ascending order (bitonic network over the list, +inf beyond ns) ...
+                int P = 1;
+                while (P < ns) P <<= 1;
+                for (int kk = 2; kk <= P; kk <<= 1) {
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const int flip = j == (kk >> 1) ? kk - 1 : j;
+                        for (int t = lane; t < (P >> 1); t += 32) {
+                            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const int l = i ^ flip;
+                            if (l < ns) {
+                                const unsigned long long a = sm.spike_key[i], b = sm.spike_key[l];
+                                if (b < a) {
+                                    sm.spike_key[i] = b;
+                                    sm.spike_key[l] = a;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ... and fast5.py:90-101, one sample after the other: out[i] = median(out[i-2:i+3]) sees the
+                // samples before i as already patched, the ones after it raw
+                if (lane == 0) {
+                    int p1i = -8, p2i = -8;
+                    int16_t p1v = 0, p2v = 0;
+                    for (int k = 0; k < ns; ++k) {
+                        const unsigned long long key = sm.spike_key[k];
+                        const int i = (int)(key >> 32), slot = (int)(key & 0xffffffffu);
+                        if (i <= 2) continue;
+                        int16_t w5[5];
+                        const int n = min(5, N - (i - 2));
+                        for (int u = 0; u < n; ++u) {
+                            const int idx = i - 2 + u;
+                            int16_t vv = sm.spike_w[slot][u];
+                            if (idx == p1i) vv = p1v;
+                            else if (idx == p2i) vv = p2v;
+                            w5[u] = vv;
+                        }
+                        const int16_t nv = median_small(w5, n);
+                        const int16_t old = sm.spike_w[slot][2];
+                        if (nv != old) hist_move(old, nv);
+                        if (i >= lo && i <= hi) stash[i - lo] = nv;
+                        p2i = p1i;
+                        p2v = p1v;
+                        p1i = i;
+                        p1v = nv;
+                    }
+                }
+            }
+        } else {
+            scan_tiles();
+        }
         atomicMin(&sm.vmin, lmin);
         atomicMax(&sm.vmax, lmax);
         __threadfence_block();
         __syncthreads();
 
-        if (warp == 0 && N > 0) {
-            // np.percentile(data, (46.5, 53.5)), method 'linear'
-            double pr[2];
-            const double qs[2] = {46.5 / 100.0, 53.5 / 100.0};
-            for (int q = 0; q < 2; ++q) {
-                const double vidx = (double)(N - 1) * qs[q];
-                int64_t i0 = (int64_t)floor(vidx), i1 = i0 + 1;
-                if (vidx >= (double)(N - 1)) i0 = i1 = N - 1;
-                const double gamma = vidx - (double)i0;
-                const int a = value_at_rank(sm, gh, i0, lane);
-                const int b = value_at_rank(sm, gh, i1, lane);
-                const int16_t diff16 = (int16_t)(b - a);              // numpy subtracts in int16
-                const double diff = (double)diff16;
-                double res = (double)a + diff * gamma;
-                if (gamma >= 0.5) res = (double)b - diff * (1.0 - gamma);
-                pr[q] = res;
+        // np.percentile(data, (46.5, 53.5)) (method 'linear'), their mean = shift, np.median(|data - shift|) = scale
+        auto percentile_from = [&](auto &&rank_value, double q) {
+            const double vidx = (double)(N - 1) * q;
+            int64_t i0 = (int64_t)floor(vidx), i1 = i0 + 1;
+            if (vidx >= (double)(N - 1)) i0 = i1 = N - 1;
+            const double gamma = vidx - (double)i0;
+            const int a = rank_value(i0);
+            const int b = rank_value(i1);
+            const int16_t diff16 = (int16_t)(b - a);              // numpy subtracts in int16
+            const double diff = (double)diff16;
+            double res = (double)a + diff * gamma;
+            if (gamma >= 0.5) res = (double)b - diff * (1.0 - gamma);
+            return res;
+        };
+        const bool by_prefix = !sm.ghist_dirty && N > 0;           // block-uniform (set before the barrier above)
+        if (by_prefix) {
+            // in-place inclusive prefix sums of hist[vmin..vmax]: a contiguous run of bins per thread, the
+            // threads' totals scanned through shared memory
+            const int v0 = sm.vmin, R = sm.vmax - sm.vmin + 1;
+            const int per = (R + NT - 1) / NT;
+            const int b0 = v0 + tid * per, b1 = min(b0 + per, v0 + R);
+            uint32_t sum = 0u;
+            for (int b = b0; b < b1; ++b) sum += sm.hist[b];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
             }
-            const double shift = (pr[0] + pr[1]) / 2.0;
+            if (lane == 31) sm.spike_bits[warp] = inc;            // (free between reads; 8 warp totals)
+            __syncthreads();
+            uint32_t base = inc - sum;
+            for (int w = 0; w < warp; ++w) base += sm.spike_bits[w];
+            for (int b = b0; b < b1; ++b) {
+                base += sm.hist[b];
+                sm.hist[b] = base;
+            }
+            __syncthreads();
+            if (tid < TILE / 32) sm.spike_bits[tid] = 0u;         // leave the bitmap clean
+            if (tid == 0) {
+                const double p0 = percentile_from([&](int64_t rk) { return value_at_rank_cum(sm, rk); }, 46.5 / 100.0);
+                const double p1 = percentile_from([&](int64_t rk) { return value_at_rank_cum(sm, rk); }, 53.5 / 100.0);
+                const double shift = (p0 + p1) / 2.0;
+                double scale;
+                if (N & 1) {
+                    scale = absdev_at_rank_cum(sm, shift, N / 2);
+                } else {
+                    const double m1 = absdev_at_rank_cum(sm, shift, N / 2 - 1);
+                    const double m2 = absdev_at_rank_cum(sm, shift, N / 2);
+                    scale = (m1 + m2) / 2.0;
+                }
+                sm.shift = shift;
+                sm.scale = scale;
+                if (p.shift_scale) {
+                    p.shift_scale[2 * r] = shift;
+                    p.shift_scale[2 * r + 1] = scale;
+                }
+            }
+        } else if (warp == 0 && N > 0) {
+            // samples outside [0, HBINS) went to the global histogram: walk the bins
+            const double p0 = percentile_from([&](int64_t rk) { return value_at_rank(sm, gh, rk, lane); }, 46.5 / 100.0);
+            const double p1 = percentile_from([&](int64_t rk) { return value_at_rank(sm, gh, rk, lane); }, 53.5 / 100.0);
+            const double shift = (p0 + p1) / 2.0;
             // np.median(np.abs(data - shift))
             double scale;
             if (N & 1) {
