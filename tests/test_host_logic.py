@@ -97,14 +97,19 @@ def test_kernel_layout_plan_invariants(built_lib):
             assert sorted(int(s) for s in sop if s >= 0) == list(range(sta.n_states))
             pos = {int(s): p for p, s in enumerate(sop) if s >= 0}
             deg = np.diff(sta.in_ptr)
-            code = info['unrolled_in_degree']           # 2 / 4, or 100 + d for the "low" layout
-            low, dmax = code >= 100, code % 100
-            assert deg.max() <= dmax
-            if low:                                     # only the last generic slot takes fan-in
-                for s_, p_ in pos.items():
-                    u_ = p_ % K
-                    if KC <= u_ < K - 1:
-                        assert deg[s_] <= 1
+            code = info['unrolled_in_degree']   # 2 / 4; 100 + d: "low" layout; 200 + 10a + b: "graded" layout
+            KGn = KG
+
+            def slot_deg(g):                    # candidates generic slot g is built with (dtw.cu: slot_deg)
+                if code >= 200:
+                    return (code - 200) // 10 if g == KGn - 1 else ((code - 200) % 10 if g == KGn - 2 else 1)
+                if code >= 100:
+                    return code - 100 if g == KGn - 1 else 1
+                return code
+            for s_, p_ in pos.items():
+                u_ = p_ % K
+                if u_ >= KC:
+                    assert deg[s_] <= slot_deg(u_ - KC), (name, s_, u_, code)
             outdeg = np.bincount(sta.in_idx, minlength=sta.n_states)
             for s, p in pos.items():
                 lane, u = divmod(p, K)

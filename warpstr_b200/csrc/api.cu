@@ -246,6 +246,16 @@ int build_layout(int S, const int32_t *in_ptr, const int32_t *in_idx, int mv, La
     for (int g : generic) (c.indeg[g] > 1 ? multi : single).push_back(g);
     const bool low = L.KG >= 2 && mv == 4 && (int)multi.size() <= 32 &&
                      (int)single.size() <= 32 * (L.KG - 1) + (32 - (int)multi.size());
+    // "graded" layout: four candidates for the last slot, two for the one before it, one for the others --
+    // when the states with three or four incoming edges fit the last slot and those with two the rest of it
+    // plus the slot before
+    std::vector<int> deg34, deg2;
+    for (int g : multi) (c.indeg[g] > 2 ? deg34 : deg2).push_back(g);
+    const int spare_last = 32 - (int)deg34.size();
+    const int deg2_in_prev = std::max(0, (int)deg2.size() - std::max(spare_last, 0));
+    const bool graded = !low && L.KG >= 3 && mv == 4 && (int)deg34.size() <= 32 && deg2_in_prev <= 32 &&
+                        (int)single.size() <= 32 * (L.KG - 2) + (32 - deg2_in_prev) +
+                                                  std::max(0, spare_last - (int)deg2.size());
     if (low) {
         // singles fill slots 0..KG-2 and then the free lanes of the last slot, in state order
         generic.clear();
@@ -254,6 +264,21 @@ int build_layout(int S, const int32_t *in_ptr, const int32_t *in_idx, int mv, La
         generic.resize(32 * (L.KG - 1), -1);
         generic.insert(generic.end(), multi.begin(), multi.end());
         generic.insert(generic.end(), single.begin() + head, single.end());
+    } else if (graded) {
+        // last slot: the states with 3-4 incoming edges, then those with two; slot before: the rest of those
+        // with two; singles fill slots 0..KG-3 and then whatever is free in the two others
+        std::vector<int> last(deg34), prev;
+        size_t d2 = 0;
+        while (d2 < deg2.size() && (int)last.size() < 32) last.push_back(deg2[d2++]);
+        while (d2 < deg2.size()) prev.push_back(deg2[d2++]);
+        size_t s1 = std::min<size_t>(single.size(), 32 * (size_t)(L.KG - 2));
+        generic.assign(single.begin(), single.begin() + s1);
+        generic.resize(32 * (size_t)(L.KG - 2), -1);
+        while (s1 < single.size() && (int)prev.size() < 32) prev.push_back(single[s1++]);
+        while (s1 < single.size() && (int)last.size() < 32) last.push_back(single[s1++]);
+        prev.resize(32, -1);
+        generic.insert(generic.end(), prev.begin(), prev.end());
+        generic.insert(generic.end(), last.begin(), last.end());
     }
     int max_indeg = 0;
     int placed = 0;
@@ -268,7 +293,7 @@ int build_layout(int S, const int32_t *in_ptr, const int32_t *in_idx, int mv, La
     }
     L.n_generic = placed;
     if (max_indeg > WSTR_MAX_DEG) return WSTR_ERR_UNSUPPORTED;
-    L.DEG = (max_indeg <= 2 ? 2 : 4) + (low ? 100 : 0);
+    L.DEG = graded ? 242 : (max_indeg <= 2 ? 2 : 4) + (low ? 100 : 0);
     return WSTR_OK;
 }
 
@@ -413,8 +438,9 @@ extern "C" int wstr_automaton_create(const double *values, const int32_t *seq_id
         d.NB = 8;
         d.RPW = 4;
     } else {                         // direction bits per lane and row (dtw.cu: DirFmt)
-        const int dmax = L.DEG >= 100 ? L.DEG - 100 : L.DEG;
-        d.NB = L.DEG >= 100 ? KC + (KG - 1) + dmax : KC + KG * dmax;
+        if (L.DEG >= 200) d.NB = KC + (KG - 2) + (L.DEG - 200) % 10 + (L.DEG - 200) / 10;
+        else if (L.DEG >= 100) d.NB = KC + (KG - 1) + (L.DEG - 100);
+        else d.NB = KC + KG * L.DEG;
         d.RPW = 32 / d.NB;
     }
     d.S = S;

@@ -124,19 +124,25 @@ __host__ __device__ constexpr int q_row_len() { return 32 * KG + 40; }
 // 10 bits, 3 rows per word = 0.17 B per cell.
 // DEG encodes the candidates per generic slot: 2 or 4 = that many for every slot; 100 + d =
 // "low" layout, one candidate for every generic slot but the last, d for the last (the host
-// puts the states with more than one incoming edge there).
+// puts the states with more than one incoming edge there); 200 + 10 a + b = "graded" layout, a
+// candidates for the last slot, b for the one before it, one for the others ((CAN): 21 states with
+// four incoming edges, 20 with two, 70 with one -- 8 candidates per lane and row instead of 16).
 template <int DEG>
 struct DegOf {
-    static constexpr bool LOW = DEG >= 100;
-    static constexpr int MAX = LOW ? DEG - 100 : DEG;
+    static constexpr bool LOW = DEG >= 100 && DEG < 200;
+    static constexpr bool GRADED = DEG >= 200;
+    static constexpr int MAX = GRADED ? (DEG - 200) / 10 : (LOW ? DEG - 100 : DEG);
 };
 template <int KG, int DEG>
 __host__ __device__ constexpr int slot_deg(int g) {
+    if (DegOf<DEG>::GRADED) return g == KG - 1 ? (DEG - 200) / 10 : (g == KG - 2 ? (DEG - 200) % 10 : 1);
     return (DegOf<DEG>::LOW && g < KG - 1) ? 1 : DegOf<DEG>::MAX;
 }
 template <int KC, int KG, int DEG>
 __host__ __device__ constexpr int slot_bit(int g) {      // first bit of generic slot g in a row's field
-    return DegOf<DEG>::LOW ? KC + g : KC + g * DegOf<DEG>::MAX;
+    int b = KC;
+    for (int i = 0; i < g; ++i) b += slot_deg<KG, DEG>(i);
+    return b;
 }
 template <int KC, int KG, int DEG>
 struct DirFmt {
@@ -455,9 +461,14 @@ __device__ __forceinline__ void traceback_warp(const DevAutomaton *A, const int 
                         nib = (f >> u) & 1u;
                     } else {
                         const int g = u - KC;
-                        const bool one = DegOf<DEG>::LOW && g < KG - 1;
-                        const int off = DegOf<DEG>::LOW ? KC + g : KC + g * DegOf<DEG>::MAX;
-                        nib = (f >> off) & (one ? 1u : (1u << DegOf<DEG>::MAX) - 1u);
+                        int off = KC, width = 1;
+#pragma unroll
+                        for (int gg = 0; gg < KG; ++gg)
+                            if (g == gg) {
+                                off = slot_bit<KC, KG, DEG>(gg);
+                                width = slot_deg<KG, DEG>(gg);
+                            }
+                        nib = (f >> off) & ((1u << width) - 1u);
                     }
                 }
                 const uint32_t moves = __ballot_sync(FULL, nib != 0u);
@@ -733,6 +744,9 @@ int launch_fill_deg(int deg, const FillParams &p, cudaStream_t s) {
     if constexpr (KG >= 2 && MV == 4) {     // low layouts: one candidate for all generic slots but the last
         if (deg == 102) return launch_fill_t<KC, KG, 102, MV>(p, s);
         if (deg == 104) return launch_fill_t<KC, KG, 104, MV>(p, s);
+    }
+    if constexpr (KG >= 3 && MV == 4) {     // graded layout: 4 candidates for the last slot, 2 for the one before
+        if (deg == 242) return launch_fill_t<KC, KG, 242, MV>(p, s);
     }
     return WSTR_ERR_UNSUPPORTED;
 }
