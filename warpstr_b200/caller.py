@@ -222,6 +222,7 @@ class CallerEngine:
         self._host_ss = None
         self._dev_cache = {}
         self._h2d_probe = None
+        self.split_small = (4096, 40000)   # batch sizes a resident call runs as two concurrent halves (None: never)
         self.ttest_guard_ulps = 0    # 0 = the library's default (16 ulp), see wstr_call_outputs.d_ttest_ties
         self.last_ttest_ties = 0     # reads of the last results_from() that were re-evaluated for a t-test tie
 
@@ -343,7 +344,7 @@ class CallerEngine:
         return d_sig, off, lengths, np.asarray(aut_ids, dtype=np.int32), np.asarray(reverse, dtype=np.uint8)
 
     def call_packed(self, d_sig, off, lengths, aut, rev, want_seq: bool = True, want_debug: bool = False,
-                    into: Optional[dict] = None, lane: int = 0):
+                    into: Optional[dict] = None, lane: int = 0, allow_split: bool = True):
         """wstr_call_batch on device-resident signals.  Returns a dict of device tensors
         (len1, len2, cost1, cost2, status, ties[, seq1, seq2, seq_off]).  A batch whose per-batch buffers
         (rescaled signal, traces, mid-stage scratch: ~35 B per sample) do not fit the workspace the memory
@@ -388,7 +389,7 @@ class CallerEngine:
                                      float(self.rc.threshold), float(self.rc.max_std),
                                      1 if self.rc.method == 'median' else 0, 1 if self.rc.reps_as_one else 0,
                                      int(self.ttest_guard_ulps))
-            for a, b in self._slices(ws.numel(), need, aut, lengths):
+            def run(a, b, wsp, stream):
                 lo = int(off[a])
                 hi = min(int(off[b - 1] + ((int(lengths[b - 1]) + 1) & ~1) + 2), d_sig.numel()) if b > a else lo
                 sl = slice(lo, hi)
@@ -397,13 +398,39 @@ class CallerEngine:
                     t = o.get(key)
                     return t[x0:x1] if t is not None else None
                 s0 = int(seq_off[a]) if want_seq else 0
-                _lib.call_batch(self.automata, aut[a:b], rev[a:b], d_sig[sl], off[a:b] - lo, lengths[a:b], params, ws,
+                _lib.call_batch(self.automata, aut[a:b], rev[a:b], d_sig[sl], off[a:b] - lo, lengths[a:b], params, wsp,
                                 o['len1'][a:b], o['len2'][a:b], o['cost1'][a:b], o['cost2'][a:b], o['status'][a:b],
                                 part('seq1', s0, None), part('seq2', s0, None),
                                 seq_off[a:b] - s0 if want_seq else None,
                                 part('trace1', lo, hi), part('trace2', lo, hi), part('rescaled', lo, hi),
-                                d_ttest_ties=o['ties'][a:b] if 'ties' in o else None)
+                                stream=stream, d_ttest_ties=o['ties'][a:b] if 'ties' in o else None)
+
+            halves = self._halves(n, lane) if allow_split else None
+            if halves is not None:
+                # A small batch is a handful of rounds of the resident warps, the last one partly empty, and
+                # four launches in a row each with such a tail.  Two halves on two streams fill each other's
+                # gaps: one half's mid-stage and kernel tails run under the other half's DP.
+                mid, side = halves
+                cur = torch.cuda.current_stream()
+                need2 = _lib.call_workspace_bytes(self.automata, aut[mid:], lengths[mid:])
+                ws2 = self._workspace(need2, 1)
+                side.wait_stream(cur)
+                run(0, mid, ws, None)
+                run(mid, n, ws2, side)
+                cur.wait_stream(side)
+            else:
+                for a, b in self._slices(ws.numel(), need, aut, lengths):
+                    run(a, b, ws, None)
         return o
+
+    def _halves(self, n: int, lane: int):
+        """(split point, side stream) when a resident call should run as two concurrent halves."""
+        import torch
+        if lane != 0 or not self.split_small or not (self.split_small[0] <= n <= self.split_small[1]):
+            return None
+        if self._lane_streams is None:
+            self._lane_streams = [torch.cuda.Stream() for _ in range(3)]
+        return n // 2, self._lane_streams[0]
 
     def _slices(self, ws_bytes: int, need: int, aut, lengths):
         """Consecutive read ranges of one call_packed: the whole batch when the workspace holds what a call
@@ -553,7 +580,7 @@ class CallerEngine:
                         into['seq1'] = dev['seq1'][int(seq_off[a]):int(seq_off[b])]
                         into['seq2'] = dev['seq2'][int(seq_off[a]):int(seq_off[b])]
                     o = self.call_packed(d_sig[lo:hi], off[a:b] - lo, lengths[a:b], aut[a:b], rev[a:b],
-                                         want_seq=want_seq, into=into, lane=lane)
+                                         want_seq=want_seq, into=into, lane=lane, allow_split=False)
                     mark(f'call{a} end', st)
                     done = torch.cuda.Event()
                     done.record(st)
