@@ -7,15 +7,22 @@
 Workload (BASELINE.json configs[1]): a synthetic batch of HD-locus reads
 `(AGC)AACAGCCGCCAC(CGC)`, AGC~U{30..45}, CGC~U{7..12}, 50 % reverse strand, dwell U{5..13},
 noise N(0, 0.15), float64, ~3.3 k samples per read, 100 000 reads per GPU (weak scaling: every
-rank gets its own 100 000 reads and its own seed; only per-read results would be gathered).
+rank gets its own 100 000 reads and its own seed; the per-read results are gathered every step).
 
 One step = the whole per-read call (two DP passes + everything between them) over the batch.
-  value : reads/s with the batch resident in HBM (wstr_call_batch on device buffers)
-  e2e   : reads/s through CallerEngine.call_arrays: pinned host signal -> H2D -> call ->
-          D2H of lengths, costs, status and decoded sequences, every step
-  roofline: the DP fill+traceback kernel against the measured FP64 add rate of this GPU
-  cpu_baseline / --impl reference: the oracle's port of the reference's Python caller on the
-          host cores (multiprocessing.Pool over reads, as CallerWrapper.run does)
+  value        reads/s with the batch resident in HBM (wstr_call_batch on device buffers)
+  e2e          reads/s from pinned host memory to host result arrays, every step: the batch as int16 window
+               samples + {shift, scale} per read (CallerEngine.call_arrays_quantized); e2e_float64 is the same
+               call on float64 windows (the reference's ReadSignal.signal), e2e_raw whole raw reads in
+               (normalised on the device)
+  roofline     the DP fill+traceback kernel against the measured FP64 add rate of this GPU
+  parity       the first 10 000 reads of the batch against the oracle (mismatch counts by kind)
+  c3, panel    strong-scaling legs through the sharded call (BASELINE configs[2] and [4]): FMR1 / (MGG) / DM2,
+               100 002 reads, and a 50-locus x 20 000-read panel, LPT-sharded over the ranks, id-keyed NCCL gather,
+               oracle sample and a sharding-independent checksum
+  cpu_baseline the oracle's port of the reference's Python caller on the host cores (kind "port")
+  --impl reference   the unmodified reference (byte-compiled to oracle/_ref) over a process pool on the host
+               cores, as CallerWrapper.run does (kind "reference")
 """
 import argparse
 import gc
