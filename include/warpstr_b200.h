@@ -128,7 +128,8 @@ int wstr_automaton_layout(const wstr_automaton *a, int32_t *state_of_pos, int32_
  * Both calls are asynchronous with respect to the host: the per-call plan (read records,
  * processing order) is written into pinned mapped memory and copied in by a kernel on `stream`;
  * no cudaMemcpy/cudaMemset is issued, so the copy engines stay free for the caller's own
- * transfers.  One CUDA device per process. */
+ * transfers.  A process may drive several devices: every call works on the current device (the one its
+ * automata were created on and its pointers belong to). */
 int64_t wstr_warp_workspace_bytes(wstr_automaton *const *automata, int32_t n_automata,
                                   const int32_t *read_automaton, const int32_t *lengths,
                                   int32_t n_reads);

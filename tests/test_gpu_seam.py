@@ -75,3 +75,23 @@ def test_call_arrays_results_do_not_alias_between_calls(built_lib):
     for k, v in first.items():
         assert np.array_equal(outs[0][k], v) and np.array_equal(again[k], v, equal_nan=True)
     assert outs[1]['status'][3] == 1 and outs[1]['len2'][3] == -1 and np.isnan(outs[1]['cost2'][3])
+
+
+def test_two_devices_in_one_process(built_lib, oracle_c):
+    """One engine per GPU in the same process, calls interleaved: the staging slots and the kernels' launch
+    attributes are per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from warpstr_b200.caller import CallerEngine
+    locus = synth.make_locus('HD', seed=81)
+    stas = [StateAutomata(locus.template_regex), StateAutomata(locus.reverse_regex)]
+    reads = synth.make_reads(locus, 12, seed=82)
+    want = [co.run_read(r.signal, co.tables_from(stas[int(r.reverse)]), 110, r.reverse, impl='c') for r in reads]
+    engines = [CallerEngine(device=f'cuda:{d}') for d in (0, 1)]
+    ids = [[e.add_automaton(s, 110) for s in stas] for e in engines]
+    for rounds in range(3):
+        for e, idd in zip(engines, ids):
+            res = e.call_batch([r.signal for r in reads], [idd[int(r.reverse)] for r in reads], [r.reverse for r in reads])
+            for g, w in zip(res, want):
+                assert (g.seq, g.resc_seq, g.cost, g.resc_cost) == (w.seq, w.resc_seq, w.cost, w.resc_cost)

@@ -550,6 +550,7 @@ struct StageSlot {
     cudaEvent_t done = nullptr;
     bool pending = false;     // its upload kernel may still be reading it
     bool reserved = false;    // handed out by stage_acquire, not yet committed
+    int dev = -1;             // device its event belongs to (the pinned buffer itself is portable)
 };
 constexpr int kStageSlots = 8;
 StageSlot g_stage[kStageSlots];
@@ -562,6 +563,8 @@ size_t g_stage_parked_bytes = 0;
 // before a fresh one is allocated: pinning host memory costs milliseconds (and serialises in the
 // kernel when several processes do it at once), so in steady state one or two slots do all the work.
 int stage_acquire(size_t bytes, StageSlot **out) {
+    int dev = 0;
+    WSTR_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_stage_mu);
     int pick = -1;
     for (int pass = 0; pass < 2 && pick < 0; ++pass) {
@@ -608,7 +611,12 @@ int stage_acquire(size_t bytes, StageSlot **out) {
         WSTR_CUDA(cudaHostAlloc(&sl.h, cap, cudaHostAllocMapped | cudaHostAllocPortable));
         sl.cap = cap;
     }
+    if (sl.done && sl.dev != dev) {       // a slot last used from another device: its event cannot be recorded here
+        cudaEventDestroy(sl.done);
+        sl.done = nullptr;
+    }
     if (!sl.done) WSTR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    sl.dev = dev;
     sl.reserved = true;
     *out = &sl;
     return WSTR_OK;

@@ -877,11 +877,13 @@ extern "C" int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off
     p.queue = reinterpret_cast<int32_t *>(ws + o_q);
     p.n_reads = n_reads;
     p.spike_mode = spike_mode;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0ull;      // devices the function attribute is set on
+    int dev = 0;
+    WSTR_CUDA(cudaGetDevice(&dev));
+    if (!((attr_done >> (dev & 63)) & 1ull)) {
         WSTR_CUDA(cudaFuncSetAttribute(normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(NormSmem)));
-        attr_set = true;
+        attr_done |= 1ull << (dev & 63);
     }
     wstr_prof_begin(2, s);
     normalize_kernel<<<grid, NT, sizeof(NormSmem), s>>>(p);

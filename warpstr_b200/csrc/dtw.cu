@@ -706,21 +706,24 @@ __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
 template <int KC, int KG, int DEG, int MV, bool MASKED>
 int launch_fill_m(const FillParams &p, cudaStream_t s) {
     static int grid_cap = 0;
+    static unsigned long long attr_done = 0ull;      // devices (by ordinal) the function attributes are set on
     const int smem = static_cast<int>(sizeof(FillSmem<KC, KG, DEG, MV>)) * WSTR_WARPS_PER_CTA;
-    if (grid_cap == 0) {
+    int dev = 0;
+    WSTR_CUDA(cudaGetDevice(&dev));
+    if (grid_cap == 0 || !((attr_done >> (dev & 63)) & 1ull)) {
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV, MASKED>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // (shared memory must not be what limits the resident warps: take the largest carve-out)
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_kernel<KC, KG, DEG, MV, MASKED>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
-        int dev = 0, sms = 0, per_sm = 0;
-        WSTR_CUDA(cudaGetDevice(&dev));
+        int sms = 0, per_sm = 0;
         WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         WSTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dtw_fill_kernel<KC, KG, DEG, MV, MASKED>,
                                                                 32 * WSTR_WARPS_PER_CTA, smem));
         if (per_sm < 1) per_sm = 1;
         grid_cap = sms * per_sm;
+        attr_done |= 1ull << (dev & 63);
     }
     int grid = (p.n + WSTR_WARPS_PER_CTA - 1) / WSTR_WARPS_PER_CTA;
     if (grid > grid_cap) grid = grid_cap;

@@ -232,14 +232,16 @@ size_t wstr_any_smem_bytes(int mv, int spad_max) { return any_smem_bytes(mv, spa
 
 int wstr_launch_fill_any(int mv, int spad_max, const FillParams &p, cudaStream_t s) {
     static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        WSTR_CUDA(cudaGetDevice(&dev));
+    static unsigned long long attr_done = 0ull;      // devices the function attributes are set on
+    int dev = 0;
+    WSTR_CUDA(cudaGetDevice(&dev));
+    if (sms == 0 || !((attr_done >> (dev & 63)) & 1ull)) {
         WSTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_any_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        WSTR_ANY_SMEM_MAX));
         WSTR_CUDA(cudaFuncSetAttribute(dtw_fill_any_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
+        attr_done |= 1ull << (dev & 63);
     }
     const size_t smem = any_smem_bytes(mv, spad_max);
     if (smem > WSTR_ANY_SMEM_MAX) return WSTR_ERR_TOO_MANY_STATES;
