@@ -98,3 +98,44 @@ def test_three_ingestion_forms_agree(built_lib, oracle_c):
         s0 = int(a['seq_off'][r])
         assert a['seq2'][s0:s0 + a['len2'][r]].tobytes().decode() == want.resc_seq
         assert a['cost2'][r] == want.resc_cost and a['cost1'][r] == want.cost
+
+
+def test_edge_inputs_of_the_array_entry_points(built_lib):
+    """A window that runs past the end of its read (numpy clips the slice), an empty window, a window shorter
+    than the dwell, empty batches."""
+    import torch
+    from warpstr_b200.caller import CallerEngine
+    locus, stas, reads = _batch(4, seed=21)
+    eng = CallerEngine()
+    ids = [eng.add_automaton(s, 110) for s in stas]
+    rng = np.random.default_rng(0)
+    raws, wins = [], []
+    for r in reads:
+        raw, lo, hi = synth.to_raw_int16(rng, r.signal, pad=512)
+        raws.append(raw)
+        wins.append((lo, hi))
+    wins[1] = (wins[1][0], len(raws[1]) + 1000)
+    wins[2] = (100, 50)
+    wins[3] = (10, 12)
+    roff = np.zeros(5, dtype=np.int64)
+    roff[1:] = np.cumsum([len(x) for x in raws])
+    aut = np.array([ids[int(r.reverse)] for r in reads], dtype=np.int32)
+    rev = np.array([r.reverse for r in reads], dtype=np.uint8)
+    res = eng.call_arrays_raw(torch.from_numpy(np.concatenate(raws)).pin_memory(), roff, [w[0] for w in wins],
+                              [w[1] for w in wins], aut, rev)
+    assert res['status'].tolist() == [0, 0, 1, 1]
+    assert res['lengths'].tolist() == [len(reads[0].signal), len(raws[1]) - wins[1][0], 0, 3]
+    assert res['len2'][2] == -1 and np.isnan(res['cost2'][3]) and res['len2'][0] > 0
+    want = no.get_data_processed(raws[1], wins[1], 'Brute')
+    x1 = co.run_read(want, co.tables_from(stas[int(rev[1])]), 110, bool(rev[1]), impl='c')
+    assert res['len2'][1] == len(x1.resc_seq) and res['cost2'][1] == x1.resc_cost
+    with pytest.raises(IndexError):                     # the reference: signal[0] / D[0, i] on an empty window
+        eng.call_raw_batch(raws, wins, [int(a) for a in aut], [bool(x) for x in rev])
+    e = np.zeros(0)
+    pin = lambda t: t.pin_memory()
+    assert eng.call_arrays(pin(torch.zeros(2, dtype=torch.float64)), e.astype(np.int64), e.astype(np.int32),
+                           e.astype(np.int32), e.astype(np.uint8))['len1'].shape == (0,)
+    assert eng.call_arrays_quantized(pin(torch.zeros(8, dtype=torch.int16)), e.astype(np.int64), e.astype(np.int32),
+                                     pin(torch.zeros((0, 2), dtype=torch.float64)), e.astype(np.int32),
+                                     e.astype(np.uint8))['len1'].shape == (0,)
+    assert eng.call_batch([], [], []) == [] and eng.call_raw_batch([], [], [], []) == []
