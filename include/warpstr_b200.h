@@ -95,7 +95,7 @@ int wstr_dequantize_batch(const int16_t *d_raw, const int64_t *raw_off, const in
  *   min_values_per_state                tr_calling_config.min_values_per_state: any value > 1, as in
  *                                       the reference (src/config.py:115).  Automata and settings the
  *                                       register-resident kernels are built for (up to 512 states, in-degree
- *                                       <= 4, min_values_per_state 2..6) run on those; everything else on the
+ *                                       <= 4, min_values_per_state 2..8) run on those; everything else on the
  *                                       catch-all kernel, same results.
  */
 int wstr_automaton_create(const double *values, const int32_t *seq_idx, const int32_t *in_ptr,

@@ -64,7 +64,7 @@ def test_catch_all_traces_match_oracle(built_lib, oracle_c, name, mv):
         assert np.array_equal(tm, oracle_c.warp(r.signal, tb, m, mv, 110)), (name, mv, r.name, 'masked')
 
 
-@pytest.mark.parametrize('mv', [2, 3, 4, 5, 6])
+@pytest.mark.parametrize('mv', [2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize('name', ['HD', 'FMR1_MGG', 'DM2', 'CAN', 'RFC1', 'C9ORF72_100'])
 def test_catch_all_equals_specialised(built_lib, name, mv):
     """The same reads through both kernels: identical traces and end costs, first and masked pass."""

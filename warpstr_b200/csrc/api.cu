@@ -115,8 +115,8 @@ struct Split {
     unsigned mv_mask;   // bit mv set = instantiated for that min_values_per_state
 };
 // keep in sync with wstr_launch_fill in dtw.cu
-const Split kSplits[] = {{7, 1, 0x10}, {6, 2, 0x7c}, {8, 1, 0x10}, {4, 4, 0x10}, {7, 2, 0x10}, {8, 2, 0x10},
-                         {6, 4, 0x7c}, {7, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
+const Split kSplits[] = {{7, 1, 0x10}, {6, 2, 0x1fc}, {8, 1, 0x10}, {4, 4, 0x10}, {7, 2, 0x10}, {8, 2, 0x10},
+                         {6, 4, 0x1fc}, {7, 4, 0x10}, {8, 4, 0x10}, {12, 4, 0x10}};
 
 struct Layout {
     int KC = 0, KG = 0, DEG = 2, n_lanes = 0, n_generic = 0;

@@ -529,7 +529,8 @@ struct alignas(16) FillSmem {
 // loads per 3-row cycle in the masked second-pass variants), and 16 warps are 2 % faster than 12.
 // The per-lane state is (KC+KG)*(MV+1) doubles; beyond 45 of them (min_values_per_state 5 or 6) the
 // loops would spill at 128 registers, so those keep the 12-warp budget; so do the layouts with two or more
-// generic slots (their candidates' addresses and values do not fit next to nine states).  So does the MASKED
+// generic slots (their candidates' addresses and values do not fit next to nine states); beyond 60 doubles of
+// state (long dwells on wide layouts) 8 warps and 255 registers.  The MASKED
 // instantiation (second pass: rows whose mask bit is set allow the shorter dwell): its extra row
 // variants spill a few values per cycle at 128 registers, which costs what the fourth warp gains
 // (41.7 ms per pass either way).  The first-pass instantiation does not contain the masked variants
@@ -542,7 +543,8 @@ struct alignas(16) FillSmem {
 #else
 #define WSTR_FILL_BOUNDS                         \
     __launch_bounds__(32 * WSTR_WARPS_PER_CTA,   \
-                      ((KC + KG) * (MV + 1) <= 45 && KG <= 1 && !MASKED ? WSTR_K8_WARPS : (KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
+                      ((KC + KG) * (MV + 1) <= 45 && KG <= 1 && !MASKED ? WSTR_K8_WARPS                                          \
+                       : ((KC + KG) * (MV + 1) <= 60 && KC + KG <= 12 ? 12 : 8)) / WSTR_WARPS_PER_CTA)
 #endif
 template <int KC, int KG, int DEG, int MV, bool MASKED>
 __global__ void WSTR_FILL_BOUNDS dtw_fill_kernel(const FillParams p) {
@@ -776,6 +778,8 @@ WSTR_DECL_PART(3)
 WSTR_DECL_PART(4)
 WSTR_DECL_PART(5)
 WSTR_DECL_PART(6)
+WSTR_DECL_PART(7)
+WSTR_DECL_PART(8)
 #undef WSTR_DECL_PART
 
 #if WSTR_HAS_PART(0)
@@ -791,7 +795,7 @@ int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaS
     typedef int (*part_fn)(int, int, int, int, const FillParams &, cudaStream_t);
     static const part_fn parts[] = {wstr_launch_fill_p0, wstr_launch_fill_p1, wstr_launch_fill_p2,
                                     wstr_launch_fill_p3, wstr_launch_fill_p4, wstr_launch_fill_p5,
-                                    wstr_launch_fill_p6};
+                                    wstr_launch_fill_p6, wstr_launch_fill_p7, wstr_launch_fill_p8};
     for (part_fn f : parts) {
         const int rc = f(kc, kg, deg, mv, p, s);
         if (rc != WSTR_ERR_UNSUPPORTED) return rc;
@@ -843,6 +847,21 @@ int wstr_launch_fill_p5(int kc, int kg, int deg, int mv, const FillParams &p, cu
 int wstr_launch_fill_p6(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
     WSTR_CASE(7, 2, 4)
     WSTR_CASE(7, 4, 4)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+// long dwells (min_values_per_state 7, 8: seven or eight running sums per state, 8 warps per SM)
+#if WSTR_HAS_PART(7)
+int wstr_launch_fill_p7(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(6, 2, 7)
+    WSTR_CASE(6, 2, 8)
+    return WSTR_ERR_UNSUPPORTED;
+}
+#endif
+#if WSTR_HAS_PART(8)
+int wstr_launch_fill_p8(int kc, int kg, int deg, int mv, const FillParams &p, cudaStream_t s) {
+    WSTR_CASE(6, 4, 7)
+    WSTR_CASE(6, 4, 8)
     return WSTR_ERR_UNSUPPORTED;
 }
 #endif
