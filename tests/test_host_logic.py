@@ -220,3 +220,14 @@ def test_pore_model_path_of_a_config(tmp_path):
     own = tmp_path / 'own.model'
     own.write_text(open(cfg.DEFAULT_PORE_MODEL).read())
     assert cfg.config_from_dict(dict(base, pore_model_path=str(own))).pore_model_path == str(own)
+
+
+def test_product_package_does_not_import_scipy_or_the_oracle():
+    """scipy is the host evaluation's dependency for flagged reads only; the oracle is test infrastructure."""
+    import subprocess
+    import sys
+    code = ("import sys; import warpstr_b200.caller, warpstr_b200.wrapper, warpstr_b200.shard, warpstr_b200.normalize; "
+            "print(sorted(m for m in sys.modules if m.split('.')[0] in ('scipy', 'oracle')))")
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and out.stdout.strip() == '[]', out.stdout + out.stderr

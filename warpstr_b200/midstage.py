@@ -1,21 +1,23 @@
-"""Host implementation of the stage between the two DP passes.
+"""Host evaluation of the stage between the two DP passes, for the reads the device flags.
 
 What the reference does between ``warp(signal)`` and ``warp(rescaled_signal, badmask)``
 (caller/caller.py:123-125 and 132-139): per-run statistics of the alignment
 (:65-96), the smoothing-spline rescale (:304-318) and the t-test segmentation that
 marks badly resolved repeat windows (:330-421).  Vectorised per read; the numpy
 reductions that decide bit-level results (pairwise ``mean``/``std`` per run,
-``splrep``/``splev``) are the same calls the reference makes.
+``splrep``/``splev``) are the same calls the reference makes, and the t-test squares with
+the host libm's ``pow`` like the reference's ``np.float64 ** 2``.
 
-This is the host path of the engine (``engine='host'``) and the fallback for
-rescaler configurations the GPU mid-stage does not cover (``reps_as_one``,
-``method: median``, splines that need interior knots).
+The device runs this stage for every configuration (``wstr_call_batch``).  This module is only
+reached for a read the device has flagged -- a smoothing spline that needs interior knots
+(``WSTR_READ_SPLINE_KNOTS``), a t-test decision within rounding distance of flipping
+(``d_ttest_ties``), a status that the reference answers with an exception (to raise its type) --
+and for ``engine='host'`` in the tests.  scipy is imported when such a read occurs, not before.
 """
 import math
 from dataclasses import dataclass
 
 import numpy as np
-from scipy import interpolate
 
 from .config import CallerConfig, RescalerConfig
 
@@ -85,6 +87,7 @@ def rescale_signal(x: np.ndarray, al: Alignment) -> np.ndarray:
     ys = al.expected[al.good]
     order = np.argsort(xs, kind='stable')
     xs, ys = xs[order], ys[order]
+    from scipy import interpolate        # only here: the product path proper never imports scipy
     try:
         tck = interpolate.splrep(xs.tolist(), ys.tolist(), s=len(xs))
     except Exception as exc:                      # FITPACK input errors (caller.py:311)
