@@ -473,19 +473,54 @@ __device__ void warp_sort_pairs_tiled(double *gkey, int32_t *gidx, int m, int la
         int j = k >> 1;
         for (; j >= CH; j >>= 1) {                            // partners in different chunks
             const int flip = j == (k >> 1) ? k - 1 : j;
-            for (int t = lane; t < (P >> 1); t += 32) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i ^ flip;
-                if (l < m) sort_cx(gkey, gidx, i, l);
+            for (int t0 = 0; t0 < (P >> 1); t0 += 128) {      // four pairs per lane in flight
+                int pi[4], pl[4];
+                double ka[4], kb[4];
+                int32_t ia[4], ib[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    pi[u] = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    pl[u] = pi[u] ^ flip;
+                    const bool on = t < (P >> 1) && pl[u] < m;
+                    if (!on) pl[u] = -1;
+                    ka[u] = on ? gkey[pi[u]] : 0.0;
+                    kb[u] = on ? gkey[pl[u]] : 0.0;
+                    ia[u] = on ? gidx[pi[u]] : 0;
+                    ib[u] = on ? gidx[pl[u]] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (pl[u] >= 0 && (kb[u] < ka[u] || (kb[u] == ka[u] && ib[u] < ia[u]))) {
+                        gkey[pi[u]] = kb[u];
+                        gkey[pl[u]] = ka[u];
+                        gidx[pi[u]] = ib[u];
+                        gidx[pl[u]] = ia[u];
+                    }
+                }
             }
             __syncwarp();
         }
         if (j == 0) continue;
         for (int c0 = 0; c0 < m; c0 += CH) {                  // partners inside one CH-aligned chunk
             const int n = min(CH, m - c0);
-            for (int e = lane; e < n; e += 32) {
-                skey[e] = gkey[c0 + e];
-                sidx[e] = gidx[c0 + e];
+            for (int e0 = 0; e0 < n; e0 += 128) {            // four loads of each array in flight per lane
+                double kk[4];
+                int32_t ii[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + 32 * u + lane;
+                    kk[u] = e < n ? gkey[c0 + e] : 0.0;
+                    ii[u] = e < n ? gidx[c0 + e] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + 32 * u + lane;
+                    if (e < n) {
+                        skey[e] = kk[u];
+                        sidx[e] = ii[u];
+                    }
+                }
             }
             __syncwarp();
             for (int jj = j; jj > 0; jj >>= 1) {
