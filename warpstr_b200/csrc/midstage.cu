@@ -444,7 +444,7 @@ __device__ __forceinline__ void sort_cx(double *key, int32_t *idx, int i, int l)
     }
 }
 
-__device__ void warp_sort_pairs(double *key, int32_t *idx, int m, int lane) {
+__device__ __forceinline__ void warp_sort_pairs(double *key, int32_t *idx, int m, int lane) {
     int P = 1;
     while (P < m) P <<= 1;
     for (int k = 2; k <= P; k <<= 1) {
@@ -718,18 +718,30 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
             __shared__ double s_key[4][SORT_SMEM];
             __shared__ int32_t s_idx[4][SORT_SMEM];
             const bool in_smem = m <= SORT_SMEM;
-            double *key = in_smem ? s_key[threadIdx.x >> 5] : sc.sx;
-            int32_t *idx = in_smem ? s_idx[threadIdx.x >> 5] : sc.sidx;
-            for (int i = lane; i < m; i += 32) {
-                key[i] = sc.px[i];
-                idx[i] = i;
-            }
-            __syncwarp();
-            if (in_smem) warp_sort_pairs(key, idx, m, lane);
-            else warp_sort_pairs_tiled<SORT_SMEM>(key, idx, m, lane, s_key[threadIdx.x >> 5], s_idx[threadIdx.x >> 5]);
-            for (int i = lane; i < m; i += 32) {
-                sc.sx[i] = key[i];
-                sc.sy[i] = sc.py[idx[i]];
+            if (in_smem) {
+                // (the shared arrays by name, so that the network's loads and stores are LDS/STS, not generic)
+                double *key = s_key[threadIdx.x >> 5];
+                int32_t *idx = s_idx[threadIdx.x >> 5];
+                for (int i = lane; i < m; i += 32) {
+                    key[i] = sc.px[i];
+                    idx[i] = i;
+                }
+                __syncwarp();
+                warp_sort_pairs(key, idx, m, lane);
+                for (int i = lane; i < m; i += 32) {
+                    sc.sx[i] = key[i];
+                    sc.sy[i] = sc.py[idx[i]];
+                }
+            } else {
+                double *key = sc.sx;
+                int32_t *idx = sc.sidx;
+                for (int i = lane; i < m; i += 32) {
+                    key[i] = sc.px[i];
+                    idx[i] = i;
+                }
+                __syncwarp();
+                warp_sort_pairs_tiled<SORT_SMEM>(key, idx, m, lane, s_key[threadIdx.x >> 5], s_idx[threadIdx.x >> 5]);
+                for (int i = lane; i < m; i += 32) sc.sy[i] = sc.py[idx[i]];
             }
             __syncwarp();
         }
