@@ -60,6 +60,36 @@ __device__ __forceinline__ double pairwise_leaf(const F &f, int start, int n) {
     return res;
 }
 
+// the same order for n <= 16 values already in registers (a run of one state: its dwell): n < 8 one after the
+// other; else eight accumulators over the first eight, the next eight added if there are sixteen, the
+// accumulators combined pairwise, the rest (n % 8 values) added one after the other
+__device__ __forceinline__ double pairwise16(const double (&w)[16], int n) {
+    if (n < 8) {
+        double res = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            if (i < n) res += w[i];
+        return res;
+    }
+    double r0 = w[0], r1 = w[1], r2 = w[2], r3 = w[3], r4 = w[4], r5 = w[5], r6 = w[6], r7 = w[7];
+    if (n == 16) {
+        r0 += w[8];
+        r1 += w[9];
+        r2 += w[10];
+        r3 += w[11];
+        r4 += w[12];
+        r5 += w[13];
+        r6 += w[14];
+        r7 += w[15];
+        return ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+#pragma unroll
+    for (int i = 8; i < 15; ++i)
+        if (i < n) res += w[i];
+    return res;
+}
+
 template <class F>
 __device__ double pairwise_sum(const F &f, int start0, int n0) {
     if (n0 <= 128) return pairwise_leaf(f, start0, n0);
@@ -614,21 +644,42 @@ __global__ void __launch_bounds__(128) mid_stats_kernel(const MidParams p) {
                 if (r < n_runs) {
                     const int a = run_start[r], n = run_start[r + 1] - a;
                     const double *xs = x + a;
-                    const double sum = pairwise_sum([xs](int i) { return xs[i]; }, 0, n);
-                    mean = sum / (double)n;
                     expect = A.values[run_state[r]];
-                    const double avg = mean;                       // np.std is taken about the mean either way
-                    if (p.method == 1) mean = run_median(xs, n);   // 'mean' is the run's state value from here on
-                    sc.sv[r] = mean;
-                    if (n >= p.mv) {
-                        const double ss = pairwise_sum(
-                            [xs, avg](int i) {
-                                const double d = xs[i] - avg;
-                                return d * d;
-                            },
-                            0, n);
-                        const double sd = sqrt(ss / (double)n);
-                        g = sd < p.max_std && fabs(expect - mean) <= p.threshold;
+                    if (n <= 16) {
+                        // the usual case: the run's samples fetched once, all loads in flight together, both
+                        // sums taken from registers
+                        double w[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) w[u] = u < n ? xs[u] : 0.0;
+                        mean = pairwise16(w, n) / (double)n;
+                        const double avg = mean;
+                        if (p.method == 1) mean = run_median(xs, n);
+                        sc.sv[r] = mean;
+                        if (n >= p.mv) {
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) {
+                                const double d = w[u] - avg;
+                                w[u] = d * d;
+                            }
+                            const double sd = sqrt(pairwise16(w, n) / (double)n);
+                            g = sd < p.max_std && fabs(expect - mean) <= p.threshold;
+                        }
+                    } else {
+                        const double sum = pairwise_sum([xs](int i) { return xs[i]; }, 0, n);
+                        mean = sum / (double)n;
+                        const double avg = mean;                       // np.std is taken about the mean either way
+                        if (p.method == 1) mean = run_median(xs, n);   // 'mean' is the run's state value from here on
+                        sc.sv[r] = mean;
+                        if (n >= p.mv) {
+                            const double ss = pairwise_sum(
+                                [xs, avg](int i) {
+                                    const double d = xs[i] - avg;
+                                    return d * d;
+                                },
+                                0, n);
+                            const double sd = sqrt(ss / (double)n);
+                            g = sd < p.max_std && fabs(expect - mean) <= p.threshold;
+                        }
                     }
                 }
                 const unsigned bal = __ballot_sync(FULL, g);
