@@ -314,6 +314,11 @@ __device__ int count_segments(const double *__restrict__ x, int c0, int c1, cons
     bool rising = false;
     double prev = 0.0;
     double m0 = 0.0, s0 = 0.0, m1 = 0.0, s1 = 0.0, m2 = 0.0, s2 = 0.0;   // right windows of c-3, c-2, c-1
+    if (c0 > c1) return -1;
+    // the right window slides by one sample per position: two of its three samples are the previous
+    // position's, the third is fetched a position ahead of its use
+    double w[3] = {x[c0], x[c0 + 1], x[c0 + 2]};
+    double nxt = c0 < c1 ? x[c0 + 3] : 0.0;
     for (int c = c0; c <= c1; ++c) {
         double ma, sa, mb, sb;
         if (c - c0 >= 3) {
@@ -322,7 +327,11 @@ __device__ int count_segments(const double *__restrict__ x, int c0, int c1, cons
         } else {
             mean_sd3<GUARD>(x + c - 3, three, ma, sa);
         }
-        mean_sd3<GUARD>(x + c, three, mb, sb);
+        mean_sd3<GUARD>(w, three, mb, sb);
+        w[0] = w[1];
+        w[1] = w[2];
+        w[2] = nxt;
+        if (c + 1 < c1) nxt = x[c + 4];
         m0 = m1; s0 = s1;
         m1 = m2; s1 = s2;
         m2 = mb; s2 = sb;
