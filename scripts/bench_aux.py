@@ -35,7 +35,8 @@ def timed(fn, reps=5):
 
 # ---- normalisation: n reads of N int16 samples, window of T samples each ---------------------------
 rng = np.random.default_rng(7)
-for n, N, T in ((4000, 150000, 3300), (20000, 60000, 3300)):
+SHAPES = ((4000, 150000, 3300),) if os.environ.get('AUX_ONLY_NORM') else ((4000, 150000, 3300), (20000, 60000, 3300))
+for n, N, T in SHAPES:
     base = (450 + 40 * rng.standard_normal(N)).astype(np.int16)
     raw = np.tile(base, n)
     raw[rng.integers(0, raw.size, raw.size // 10000)] = 1500       # spikes
@@ -48,12 +49,26 @@ for n, N, T in ((4000, 150000, 3300), (20000, 60000, 3300)):
     d_ss = torch.empty(2 * n, dtype=torch.float64, device='cuda')
     ws = torch.empty(_lib.normalize_workspace_bytes(n), dtype=torch.uint8, device='cuda')
     ms = timed(lambda: _lib.normalize_batch(d_raw, raw_off, lo, hi, 1, d_out, out_off, d_ss, ws))
+    if os.environ.get('AUX_NORM_PHASES'):        # a -DWSTR_NORM_TIMING build: clock64 ticks per phase, summed over CTAs
+        import ctypes
+        lib = ctypes.CDLL(_lib.LIB_PATH)
+        buf = (ctypes.c_ulonglong * 8)()
+        lib.wstr_debug_norm_phases(buf, 1)
+        _lib.normalize_batch(d_raw, raw_off, lo, hi, 1, d_out, out_off, d_ss, ws)
+        torch.cuda.synchronize()
+        lib.wstr_debug_norm_phases(buf, 0)
+        tot = float(sum(buf)) or 1.0
+        names = ['-', 'meta+estimate', 'scan', 'patch', 'reduce', 'stats', 'convert', 'queue']
+        print(json.dumps({'norm_phase_share': {k: round(v / tot, 3) for k, v in zip(names, buf) if k != '-'},
+                          'ticks_per_read': {k: int(v / n) for k, v in zip(names, buf) if k != '-'}}))
     alg = raw.nbytes + n * T * 8                                    # 2 B/raw sample read once + 8 B/window sample written
     print(json.dumps({'kernel': 'normalize_kernel', 'reads': n, 'samples_per_read': N, 'window': T, 'ms': ms,
                       'algorithmic_bytes': alg, 'achieved_gbs': alg / ms / 1e6, 'peak_gbs': peak,
                       'frac': alg / ms / 1e6 / peak, 'reads_per_s': n / ms * 1e3}))
     del d_raw, d_out
 
+if os.environ.get('AUX_ONLY_NORM'):
+    sys.exit(0)
 # ---- pore lookup: one long sequence ---------------------------------------------------------------------
 pm = get_pore_model()
 L = 1 << 26

@@ -14,13 +14,13 @@ objdir = os.path.join(ROOT, 'build', 'variant_' + name)
 os.makedirs(objdir, exist_ok=True)
 objs, procs = [], []
 only_aux = any('WSTR_NORM' in e for e in extra)
-for name, unit_flags, objname in g.units():
-    src = os.path.join(g.CSRC, name)
+for unit, unit_flags, objname in g.units():
+    src = os.path.join(g.CSRC, unit)
     obj = os.path.join(objdir, objname)
     objs.append(obj)
     # only dtw.cu (or aux.cu for the WSTR_NORM_* knobs) depends on the experiment knobs; reuse the stock objects for the rest
     stock = os.path.join(ROOT, 'build', objname)
-    if (name != ('aux.cu' if only_aux else 'dtw.cu')) and os.path.exists(stock) and not any('WARPS_PER_CTA' in e for e in extra):
+    if (unit != ('aux.cu' if only_aux else 'dtw.cu')) and os.path.exists(stock) and not any('WARPS_PER_CTA' in e for e in extra):
         objs[-1] = stock
         continue
     procs.append(subprocess.Popen([g._nvcc()] + g.NVCC_FLAGS + unit_flags + extra + ['-c', src, '-o', obj]))

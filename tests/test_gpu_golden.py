@@ -106,6 +106,45 @@ def test_normalisation_edges(built_lib, mode):
         assert np.array_equal(g, want, equal_nan=True), (len(r), w, mode)
 
 
+@pytest.mark.parametrize('mode', ['None', 'Brute'])
+def test_normalisation_window_histogram_and_its_fallback(built_lib, mode):
+    """Brute / None count the samples in a 512-value window around an estimate of the read's median
+    (one counter column per lane); a read whose order statistics fall outside that window is redone on
+    the value-indexed histogram.  Narrow, wide, bimodal, constant, drifting and off-scale reads, with
+    and without spikes: all bit-equal to numpy."""
+    from oracle import normalize_oracle as no
+    from warpstr_b200.normalize import normalize_windows
+    rng = np.random.default_rng(31 + len(mode))
+    raws = []
+    for n in (37, 2048, 5000, 40000, 150001):
+        t = np.arange(n)
+        raws += [
+            (470 + 28 * rng.standard_normal(n)).astype(np.int16),                       # a real read's spread
+            (500 + 110 * rng.standard_normal(n)).astype(np.int16),                      # tails outside the window
+            np.where(rng.random(n) < 0.5, 260, 940).astype(np.int16),                   # bimodal: MAD outside it
+            np.where(rng.random(n) < 0.48, 300 + rng.integers(0, 5, n), 800).astype(np.int16),
+            np.full(n, 512, dtype=np.int16),                                            # scale 0 -> inf / nan
+            (300 + 500 * t / n + 10 * rng.standard_normal(n)).astype(np.int16),         # drift across the read
+            (9000 + 30 * rng.standard_normal(n)).astype(np.int16),                      # beyond the 8192-bin histogram
+            (-200 + 30 * rng.standard_normal(n)).astype(np.int16),                      # negative
+            np.concatenate((np.full(n // 2, 300), np.full(n - n // 2, 811))).astype(np.int16),   # estimate far off
+            rng.integers(-32768, 32767, size=n).astype(np.int16),                       # the whole int16 range
+        ]
+    for i, r in enumerate(raws):
+        if i % 2 == 0 and len(r) > 100:
+            r[rng.integers(3, len(r), max(len(r) // 3000, 3))] = rng.choice([1500, 90, 30000])
+    r = (470 + 28 * rng.standard_normal(30000)).astype(np.int16)                        # more spikes than the list holds
+    r[rng.integers(3, len(r), 600)] = 1400
+    raws.append(r)
+    wins = [(int(rng.integers(0, max(len(r) - 3000, 1))), 0) for r in raws]
+    wins = [(lo, lo + 2999) for lo, _ in wins]
+    with np.errstate(all='ignore'):
+        got = normalize_windows(raws, wins, mode, return_shift_scale=True)
+        for i, (r, w) in enumerate(zip(raws, wins)):
+            want = no.get_data_processed(r, w, mode)
+            assert np.array_equal(got[0][i], want, equal_nan=True), (i, len(r), mode)
+
+
 def test_pore_lookup_edges(built_lib):
     """Every length around the 4-outputs-per-thread grouping, invalid characters at every offset,
     an output buffer that is not 16-byte aligned."""

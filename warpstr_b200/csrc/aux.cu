@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include "wstr_internal.h"
+#include <type_traits>
 
 // ------------------------------------------------------------------------------------------
 // (1) pore-model lookup
@@ -179,13 +180,39 @@ extern "C" int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d
 // ------------------------------------------------------------------------------------------
 // (2) normalisation
 // ------------------------------------------------------------------------------------------
+#ifdef WSTR_NORM_TIMING
+__device__ unsigned long long g_norm_phase[8];
+#define WSTR_NORM_T(i)                                                      \
+    do {                                                                    \
+        if (threadIdx.x == 0) {                                             \
+            const long long now_ = clock64();                               \
+            if ((i) > 0) atomicAdd(&g_norm_phase[i], (unsigned long long)(now_ - t_phase_)); \
+            else if (t_phase_) atomicAdd(&g_norm_phase[7], (unsigned long long)(now_ - t_phase_)); \
+            t_phase_ = now_;                                                \
+        }                                                                   \
+    } while (0)
+extern "C" int wstr_debug_norm_phases(unsigned long long *out8, int reset) {
+    if (reset) {
+        unsigned long long z[8] = {0};
+        return (int)cudaMemcpyToSymbol(g_norm_phase, z, sizeof(z));
+    }
+    return (int)cudaMemcpyFromSymbol(out8, g_norm_phase, 8 * sizeof(unsigned long long));
+}
+#else
+#define WSTR_NORM_T(i)
+#endif
 namespace {
 
 constexpr int NT = 256;              // threads per CTA
 constexpr int PER = 8;               // samples per thread per tile
 constexpr int TILE = NT * PER;       // 2048
-constexpr int HBINS = 8192;          // shared histogram covers values [0, HBINS)
+constexpr int HBINS = 8192;          // shared histogram (general path) covers values [0, HBINS)
+constexpr int WBINS = 384;           // window histogram (Brute / None): values [wlo, wlo + WBINS), one column per lane
 constexpr int GBINS = 65536;         // global fallback histogram covers every int16
+#ifndef WSTR_NORM_DEPTH
+#define WSTR_NORM_DEPTH 4            // tiles in flight per CTA
+#endif
+constexpr int NSTAGE = WSTR_NORM_DEPTH + 1;   // tiles of shared memory the window scan's bulk copies rotate through
 constexpr int SPIKE_CAP = 256;       // out-of-range samples of one read the barrier-free path can hold
 
 struct NormParams {
@@ -202,24 +229,39 @@ struct NormParams {
 };
 
 struct NormSmem {
-    uint32_t hist[HBINS];
-    // tile[HALO + t] = sample t of the current tile; tile[HALO-2], tile[HALO-1] = the two
+    // general path: hist[v], v in [0, HBINS).  Window path: hist[(v - wlo) * 32 + lane] -- every lane of a
+    // warp counts into its own bank, so the eight increments a thread issues per step never meet a bank
+    // conflict (a value-indexed histogram costs ~3.5 replays per warp instruction on random values).
+    alignas(16) uint32_t hist[WBINS * 32];
+    // Window path: NSTAGE tiles of raw samples, filled by bulk asynchronous copies (one thread issues,
+    // every thread reads its eight samples back with one 16-byte load).  Tile path and the final
+    // conversion: tile[HALO + t] = sample t of the current tile; tile[HALO-2], tile[HALO-1] = the two
     // (patched) samples before it.  HALO = 8 keeps the tile 16-byte aligned for vector access.
-    alignas(16) int16_t tile[TILE + 16];
+    union {
+        alignas(128) int16_t stage[NSTAGE * TILE];
+        alignas(16) int16_t tile[TILE + 16];
+    };
+    alignas(8) uint64_t full[NSTAGE], empty[NSTAGE];
     uint32_t spike_bits[TILE / 32];  // Brute, tile path: out-of-range samples of the current tile (all zero between tiles)
     // Brute, barrier-free path: the out-of-range samples of the read, (index << 32 | slot) for sorting, and
     // the raw samples i-2 .. i+2 around each, fetched by the thread that found it
     unsigned long long spike_key[SPIKE_CAP];
     int16_t spike_w[SPIKE_CAP][5];
+    int16_t spike_nv[SPIKE_CAP];     // window path: the samples' values after patching
     int32_t n_spikes;
     int32_t next_read;
+    int32_t wlo, below, above;       // window path: first value of the window, samples under / over it
+    int32_t win_ok, old_dirty;
     int32_t vmin, vmax;
     int32_t ghist_dirty;
     double shift, scale;
 };
 constexpr int HALO = 8;
+#ifndef WSTR_NORM_EXP
+#define WSTR_NORM_EXP 0
+#endif
 #ifndef WSTR_NORM_BLOCKS
-#define WSTR_NORM_BLOCKS 5          // resident CTAs per SM the register budget is set for (48 registers)
+#define WSTR_NORM_BLOCKS 3          // resident CTAs per SM (75 KB of shared memory each)
 #endif
 
 __device__ __forceinline__ uint32_t hcount(const NormSmem &sm, const uint32_t *gh, int v) {
@@ -334,6 +376,130 @@ __device__ double absdev_at_rank_cum(const NormSmem &sm, double shift, int64_t r
     return within < sch ? du : dl;
 }
 
+__device__ __forceinline__ uint32_t nsmem_u32(const void *q) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(q));
+}
+__device__ __forceinline__ void nbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nsmem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nsmem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool nbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(nsmem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// one thread: announce `bytes` on `bar` and start the bulk copy global -> shared (TMA engine; no register or L1
+// staging: with three 75 KB CTAs on an SM the L1 left over is too small to hold a deep queue of 16-byte loads)
+__device__ __forceinline__ void nbulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nsmem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     nsmem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(nsmem_u32(bar))
+                 : "memory");
+}
+
+struct NormCtx {
+    const int16_t *raw;
+    int16_t *stash;
+    uint32_t *gh;
+    int N, lo, hi, mis, wlo, spike_mode, tid;
+};
+
+// One thread's eight samples of tile k of the barrier-free scan, no assumption made: the tile may hang over either
+// end of the read or meet the output window, samples may be Brute's to patch (noted in the spike list with their
+// neighbourhoods) or lie outside the histogram.  WIN: the lane-column window histogram, returns (samples under the
+// window) | (samples over it) << 8; otherwise the value-indexed histogram with the global one behind it, returns
+// (min & 0xffff) | max << 16 of the valid samples.
+template <bool WIN>
+__device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, const uint4 loaded, const int k) {
+    union {
+        uint4 q;
+        int16_t h[PER];
+    } cur;
+    cur.q = loaded;
+    const int N = c.N, lo = c.lo, hi = c.hi, wlo = c.wlo;
+    const int t_base = k * TILE - c.mis;
+    const int g0 = t_base + c.tid * PER;
+    const bool in_window = t_base <= hi && t_base + TILE > lo;
+    int tmin = 32767, tmax = -32768;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int g = g0 + u;
+        if (g >= 0 && g < N) {
+            tmin = min(tmin, (int)cur.h[u]);
+            tmax = max(tmax, (int)cur.h[u]);
+        }
+    }
+    if (c.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {       // note where Brute will patch
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int g = g0 + u;
+            if (g >= 0 && g < N && (cur.h[u] > 1000 || cur.h[u] < 250)) {
+                const int pos = atomicAdd(&sm.n_spikes, 1);
+                if (pos < SPIKE_CAP) {
+                    if (WIN) {                                    // (the neighbourhoods are fetched after the scan)
+                        reinterpret_cast<uint32_t *>(sm.spike_key)[pos] = (uint32_t)g;
+                    } else {
+                        sm.spike_key[pos] = ((unsigned long long)(unsigned)g << 32) | (unsigned)pos;
+#pragma unroll
+                        for (int d = 0; d < 5; ++d) {
+                            const int idx = g - 2 + d;
+                            sm.spike_w[pos][d] = (idx >= 0 && idx < N) ? c.raw[idx] : (int16_t)0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    int ret;
+    if (WIN) {
+        uint32_t *const col = sm.hist + (c.tid & 31) - wlo * 32;
+        int below = 0, above = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int g = g0 + u;
+            if (g < 0 || g >= N) continue;
+            const int vv = cur.h[u];
+            if (vv < wlo) ++below;
+            else if (vv >= wlo + WBINS) ++above;
+            else atomicAdd(col + vv * 32, 1u);
+        }
+        ret = below | above << 8;
+    } else {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int g = g0 + u;
+            if (g < 0 || g >= N) continue;
+            const int vv = cur.h[u];
+            if (vv >= 0 && vv < HBINS) {
+                atomicAdd(&sm.hist[vv], 1u);
+            } else {
+                atomicAdd(&c.gh[vv + 32768], 1u);
+                sm.ghist_dirty = 1;
+            }
+        }
+        ret = (tmin & 0xffff) | tmax << 16;
+    }
+    if (!WIN && in_window) {                                      // (the window form converts straight from the read)
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int g = g0 + u;
+            if (g >= lo && g <= hi && g < N) c.stash[g - lo] = cur.h[u];
+        }
+    }
+    return ret;
+}
+
 // One CTA per read, one pass over the samples, 2048 per step.  The read is walked from the
 // 16-byte boundary at or before its first sample, so every thread loads its 8 samples with one
 // aligned 16-byte load, a step ahead of their use (samples in front of / behind the read are
@@ -352,11 +518,27 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
     NormSmem &sm = *reinterpret_cast<NormSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *gh = p.ghist + (size_t)blockIdx.x * GBINS;
+    uint32_t *const cum = reinterpret_cast<uint32_t *>(sm.tile);   // window path: prefix sums of the window's bins
 
+    // the window path finds its histogram zero and leaves it zero
+    for (int b = tid; b < WBINS * 32; b += NT) sm.hist[b] = 0u;
+    if (tid == 0) {
+        sm.old_dirty = 0;
+        for (int b = 0; b < NSTAGE; ++b) {
+            nbar_init(&sm.full[b], 1);
+            nbar_init(&sm.empty[b], NT);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t jstep = 0;              // window-scan steps so far (all reads): stage = jstep % NSTAGE, use = jstep / NSTAGE
+
+    long long t_phase_ = 0;
+    (void)t_phase_;
     for (;;) {
         if (tid == 0) sm.next_read = atomicAdd(p.queue, 1);
         __syncthreads();
         const int r = sm.next_read;
+        WSTR_NORM_T(0);
         if (r >= p.n_reads) break;
         const int16_t *raw = p.raw + p.raw_off[r];
         // (a read has fewer than 2^31 - 2*TILE samples, checked by the host: tile-relative indices fit an int)
@@ -366,16 +548,18 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         double *out = p.out + p.out_off[r];
         int16_t *stash = reinterpret_cast<int16_t *>(out) + 3 * (int64_t)Tw;   // tail of the output window
 
-        for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
+        const bool try_window = p.spike_mode <= 1;
+        if (try_window && sm.old_dirty)                                  // (block-uniform: written before a barrier)
+            for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
         if (tid == 0) {
-            sm.vmin = 32767;
-            sm.vmax = -32768;
-            sm.ghist_dirty = 0;
             sm.n_spikes = 0;
+            sm.below = 0;
+            sm.above = 0;
+            sm.win_ok = 0;
+            sm.ghist_dirty = 0;
         }
-        if (tid < HALO) sm.tile[tid] = 0;
-        if (tid < TILE / 32) sm.spike_bits[tid] = 0u;
         __syncthreads();
+        if (tid == 0 && try_window) sm.old_dirty = 0;
 
         // sample index g (0-based in the read) of tile k, thread tid, element u: k*TILE + tid*PER + u - mis
         const int mis = (int)((reinterpret_cast<uintptr_t>(raw) >> 1) & 7);
@@ -387,81 +571,161 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             return v < n_vec ? __ldg(vec + v) : make_uint4(0u, 0u, 0u, 0u);
         };
         int lmin = 32767, lmax = -32768;
-        // ---- barrier-free scan (Brute / None) -----------------------------------------------------
-        auto scan_fast = [&]() {
-            uint4 nxt = fetch(0), nxt2 = fetch(1);                 // two steps of loads in flight per thread
+        // np.percentile(data, q) (method 'linear') from a rank -> value function
+        auto percentile_from = [&](auto &&rank_value, double q) {
+            const double vidx = (double)(N - 1) * q;
+            int64_t i0 = (int64_t)floor(vidx), i1 = i0 + 1;
+            if (vidx >= (double)(N - 1)) i0 = i1 = N - 1;
+            const double gamma = vidx - (double)i0;
+            const int a = rank_value(i0);
+            const int b = rank_value(i1);
+            const int16_t diff16 = (int16_t)(b - a);              // numpy subtracts in int16
+            const double diff = (double)diff16;
+            double res = (double)a + diff * gamma;
+            if (gamma >= 0.5) res = (double)b - diff * (1.0 - gamma);
+            return res;
+        };
+        // ---- barrier-free scans (Brute / None) ------------------------------------------------------------
+        NormCtx ctx;
+        ctx.raw = raw;
+        ctx.stash = stash;
+        ctx.gh = gh;
+        ctx.N = N;
+        ctx.lo = lo;
+        ctx.hi = hi;
+        ctx.mis = mis;
+        ctx.wlo = 0;
+        ctx.spike_mode = p.spike_mode;
+        ctx.tid = tid;
+        int n_below = 0, n_above = 0;
+        // Window form.  The loop body is what a step is for nearly every tile of nearly every read -- the
+        // thread's eight samples all inside the window (and inside [250, 1000] for Brute), the tile whole and
+        // not meeting the output window: min/max two samples per instruction, eight increments -- and is kept
+        // that small on purpose; everything else is one out-of-line call.
+        // tile k of this read is step j of the kernel: stage j % NSTAGE, its (j / NSTAGE)-th use
+        auto issue = [&](int k, uint32_t j) {                     // (thread 0)
+            const uint32_t st = j % NSTAGE, use = j / NSTAGE;
+            if (use > 0)
+                while (!nbar_try_wait(&sm.empty[st], (use - 1) & 1u)) {
+                }
+            const int bytes = min(TILE * 2, n_vec * 16 - k * (TILE * 2));
+            nbulk_load(&sm.stage[st * TILE], reinterpret_cast<const char *>(vec) + (size_t)k * (TILE * 2),
+                       (uint32_t)bytes, &sm.full[st]);
+        };
+        auto scan_window_prologue = [&]() {                       // (thread 0; the copies overlap the estimate below)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was last written by threads
+            for (int d = 0; d < NSTAGE - 1; ++d)
+                if (d < n_tiles) issue(d, jstep + d);
+        };
+        auto scan_window = [&]() {
+            const int wlo = sm.wlo;
+            ctx.wlo = wlo;
+            uint32_t *const col = sm.hist + lane - wlo * 32;     // col[v * 32] = this lane's counter of value v
+            const int ok_lo = p.spike_mode == 1 ? max(wlo, 250) : wlo;
+            const int ok_hi = p.spike_mode == 1 ? min(wlo + WBINS - 1, 1000) : wlo + WBINS - 1;
             for (int k = 0; k < n_tiles; ++k) {
+                const uint32_t j = jstep + k, st = j % NSTAGE, use = j / NSTAGE;
+                while (!nbar_try_wait(&sm.full[st], use & 1u)) {
+                }
                 union {
                     uint4 q;
                     int16_t h[PER];
                 } cur;
-                cur.q = nxt;
-                nxt = nxt2;
-                nxt2 = fetch(k + 2);
+                cur.q = *reinterpret_cast<const uint4 *>(&sm.stage[st * TILE + tid * PER]);
+                nbar_arrive(&sm.empty[st]);
+                // the stage tile k - 1 was in goes to tile k - 1 + NSTAGE (everybody has to have read it: most have)
+                if (tid == 0 && k + NSTAGE - 1 < n_tiles) issue(k + NSTAGE - 1, j + NSTAGE - 1);
                 const int t_base = k * TILE - mis;
-                const int g0 = t_base + tid * PER;
-                const bool interior = t_base >= 0 && t_base + TILE <= N;
-                const bool in_window = t_base <= hi && t_base + TILE > lo;
-                int tmin, tmax;
-                if (interior) {
-                    const unsigned mn = __vmins2(__vmins2(cur.q.x, cur.q.y), __vmins2(cur.q.z, cur.q.w));
-                    const unsigned mx = __vmaxs2(__vmaxs2(cur.q.x, cur.q.y), __vmaxs2(cur.q.z, cur.q.w));
-                    tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
-                    tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
-                } else {
-                    tmin = 32767;
-                    tmax = -32768;
-#pragma unroll
-                    for (int u = 0; u < PER; ++u) {
-                        const int g = g0 + u;
-                        if (g >= 0 && g < N) {
-                            tmin = min(tmin, (int)cur.h[u]);
-                            tmax = max(tmax, (int)cur.h[u]);
-                        }
-                    }
+                const bool plain = t_base >= 0 && t_base + TILE <= N;
+                const unsigned mn = __vmins2(__vmins2(cur.q.x, cur.q.y), __vmins2(cur.q.z, cur.q.w));
+                const unsigned mx = __vmaxs2(__vmaxs2(cur.q.x, cur.q.y), __vmaxs2(cur.q.z, cur.q.w));
+                const int tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
+                const int tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
+#if WSTR_NORM_EXP == 8
+                if (plain) {
+                    n_below += tmin + tmax;
+                    continue;
                 }
-                if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {       // note where Brute will patch
+#elif WSTR_NORM_EXP == 9
+                n_below += tmin + tmax;
+                continue;
+#endif
+                if (plain && tmin >= ok_lo && tmax <= ok_hi) {
 #pragma unroll
-                    for (int u = 0; u < PER; ++u) {
-                        const int g = g0 + u;
-                        if (g >= 0 && g < N && (cur.h[u] > 1000 || cur.h[u] < 250)) {
-                            const int pos = atomicAdd(&sm.n_spikes, 1);
-                            if (pos < SPIKE_CAP) {
-                                sm.spike_key[pos] = ((unsigned long long)(unsigned)g << 32) | (unsigned)pos;
-#pragma unroll
-                                for (int d = 0; d < 5; ++d) {
-                                    const int idx = g - 2 + d;
-                                    sm.spike_w[pos][d] = (idx >= 0 && idx < N) ? raw[idx] : (int16_t)0;
-                                }
+#if WSTR_NORM_EXP == 1
+                    for (int u = 0; u < PER; ++u) atomicAdd(sm.hist + ((int)cur.h[u] - wlo), 1u);
+#elif WSTR_NORM_EXP == 2
+                    for (int u = 0; u < PER; ++u) n_below += cur.h[u] == 12345;
+#else
+                    for (int u = 0; u < PER; ++u) atomicAdd(col + (int)cur.h[u] * 32, 1u);
+#endif
+                } else {
+                    const int ba = norm_step_general<true>(sm, ctx, cur.q, k);
+                    n_below += ba & 0xff;
+                    n_above += ba >> 8;
+                }
+            }
+            jstep += (uint32_t)n_tiles;
+        };
+        // Value-indexed form (the reads the window did not hold): every step out of line.
+        auto scan_fast = [&]() {
+            uint4 nxt = fetch(0);
+            for (int k = 0; k < n_tiles; ++k) {
+                const uint4 q = nxt;
+                nxt = fetch(k + 1);
+                const int mm = norm_step_general<false>(sm, ctx, q, k);
+                lmin = min(lmin, (int)(int16_t)(mm & 0xffff));
+                lmax = max(lmax, mm >> 16);
+            }
+        };
+        // warp 0, after a barrier: the noted out-of-range samples in ascending order (bitonic network over the
+        // list, +inf beyond ns), then fast5.py:90-101 one sample after the other by one lane: out[i] =
+        // median(out[i-2:i+3]) sees the samples before i as already patched, the ones after it raw.
+        // move(old, new) takes the sample from one histogram bin to another.
+        auto patch_spikes = [&](int ns, auto &&move) {
+            int P = 1;
+            while (P < ns) P <<= 1;
+            for (int kk = 2; kk <= P; kk <<= 1) {
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const int flip = j == (kk >> 1) ? kk - 1 : j;
+                    for (int t = lane; t < (P >> 1); t += 32) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int l = i ^ flip;
+                        if (l < ns) {
+                            const unsigned long long a = sm.spike_key[i], b = sm.spike_key[l];
+                            if (b < a) {
+                                sm.spike_key[i] = b;
+                                sm.spike_key[l] = a;
                             }
                         }
                     }
+                    __syncwarp();
                 }
-                lmin = min(lmin, tmin);
-                lmax = max(lmax, tmax);
-                if (interior && tmin >= 0 && tmax < HBINS) {
-#pragma unroll
-                    for (int u = 0; u < PER; ++u) atomicAdd(&sm.hist[cur.h[u]], 1u);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < PER; ++u) {
-                        const int g = g0 + u;
-                        if (g < 0 || g >= N) continue;
-                        const int vv = cur.h[u];
-                        if (vv >= 0 && vv < HBINS) {
-                            atomicAdd(&sm.hist[vv], 1u);
-                        } else {
-                            atomicAdd(&gh[vv + 32768], 1u);
-                            sm.ghist_dirty = 1;
-                        }
+            }
+            if (lane == 0) {
+                int p1i = -8, p2i = -8;
+                int16_t p1v = 0, p2v = 0;
+                for (int k = 0; k < ns; ++k) {
+                    const unsigned long long key = sm.spike_key[k];
+                    const int i = (int)(key >> 32), slot = (int)(key & 0xffffffffu);
+                    if (i <= 2) continue;
+                    int16_t w5[5];
+                    const int n = min(5, N - (i - 2));
+                    for (int u = 0; u < n; ++u) {
+                        const int idx = i - 2 + u;
+                        int16_t vv = sm.spike_w[slot][u];
+                        if (idx == p1i) vv = p1v;
+                        else if (idx == p2i) vv = p2v;
+                        w5[u] = vv;
                     }
-                }
-                if (in_window) {
-#pragma unroll
-                    for (int u = 0; u < PER; ++u) {
-                        const int g = g0 + u;
-                        if (g >= lo && g <= hi && g < N) stash[g - lo] = cur.h[u];
-                    }
+                    const int16_t nv = median_small(w5, n);
+                    const int16_t old = sm.spike_w[slot][2];
+                    if (nv != old) move((int)old, (int)nv);
+                    if (i >= lo && i <= hi) stash[i - lo] = nv;
+                    p2i = p1i;
+                    p2v = p1v;
+                    p1i = i;
+                    p1v = nv;
                 }
             }
         };
@@ -635,24 +899,43 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         }
         };
 
-        if (p.spike_mode <= 1) {
-            scan_fast();
+        // ---- window path (Brute / None) -------------------------------------------------------------------
+        bool done = false;
+        int win_ns = 0;
+        if (try_window) {
+            // where the window goes: the median of 32 samples spread over the read (warp 0, each lane ranks
+            // its own sample), WBINS / 2 under it
+            if (tid == 0) scan_window_prologue();
+            if (warp == 0) {
+                const int mine = raw[(int)(((int64_t)lane * N) >> 5)];
+                int rank = 0;
+#pragma unroll
+                for (int o = 0; o < 32; ++o) {
+                    const int other = __shfl_sync(0xffffffffu, mine, o);
+                    rank += (other < mine || (other == mine && o < lane)) ? 1 : 0;
+                }
+                if (rank == 16) sm.wlo = mine - WBINS / 2;
+            }
             __syncthreads();
+        WSTR_NORM_T(1);
+            scan_window();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                n_below += __shfl_xor_sync(0xffffffffu, n_below, o);
+                n_above += __shfl_xor_sync(0xffffffffu, n_above, o);
+            }
+            if (lane == 0 && (n_below | n_above)) {
+                atomicAdd(&sm.below, n_below);
+                atomicAdd(&sm.above, n_above);
+            }
+            __syncthreads();
+        WSTR_NORM_T(2);
+            const int wlo = sm.wlo;
             const int ns = sm.n_spikes;
-            if (ns > SPIKE_CAP) {
-                // too many for the list: start over on the tile path
-                __syncthreads();
-                for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
-                if (sm.ghist_dirty)
-                    for (int b = tid; b < GBINS; b += NT) gh[b] = 0u;
-                lmin = 32767;
-                lmax = -32768;
-                __syncthreads();
-                if (tid == 0) sm.ghist_dirty = 0;
-                __syncthreads();
-                scan_tiles();
-            } else if (ns > 0 && warp == 0) {
-                // ascending order (bitonic network over the list, +inf beyond ns) ...
+            win_ns = ns;
+            uint32_t *const sidx = reinterpret_cast<uint32_t *>(sm.spike_key);   // the noted samples' indices
+            if (ns > 0 && ns <= SPIKE_CAP && warp == 0) {
+                // Brute (fast5.py:90-101) on the noted samples.  Ascending order (bitonic network, +inf beyond ns) ...
                 int P = 1;
                 while (P < ns) P <<= 1;
                 for (int kk = 2; kk <= P; kk <<= 1) {
@@ -662,77 +945,100 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                             const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                             const int l = i ^ flip;
                             if (l < ns) {
-                                const unsigned long long a = sm.spike_key[i], b = sm.spike_key[l];
-                                if (b < a) {
-                                    sm.spike_key[i] = b;
-                                    sm.spike_key[l] = a;
+                                const uint32_t a = sidx[i], b2 = sidx[l];
+                                if (b2 < a) {
+                                    sidx[i] = b2;
+                                    sidx[l] = a;
                                 }
                             }
                         }
                         __syncwarp();
                     }
                 }
-                // ... and fast5.py:90-101, one sample after the other: out[i] = median(out[i-2:i+3]) sees the
-                // samples before i as already patched, the ones after it raw
-                if (lane == 0) {
-                    int p1i = -8, p2i = -8;
-                    int16_t p1v = 0, p2v = 0;
-                    for (int k = 0; k < ns; ++k) {
-                        const unsigned long long key = sm.spike_key[k];
-                        const int i = (int)(key >> 32), slot = (int)(key & 0xffffffffu);
-                        if (i <= 2) continue;
-                        int16_t w5[5];
-                        const int n = min(5, N - (i - 2));
-                        for (int u = 0; u < n; ++u) {
-                            const int idx = i - 2 + u;
-                            int16_t vv = sm.spike_w[slot][u];
-                            if (idx == p1i) vv = p1v;
-                            else if (idx == p2i) vv = p2v;
-                            w5[u] = vv;
+                // ... the raw samples i-2 .. i+2 around each, all loads in flight at once ...
+                for (int t = lane; t < ns; t += 32) {
+                    const int i = (int)sidx[t];
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) {
+                        const int idx = i - 2 + d;
+                        sm.spike_w[t][d] = (idx >= 0 && idx < N) ? raw[idx] : (int16_t)0;
+                    }
+                }
+                __syncwarp();
+                // ... and out[i] = median(out[i-2:i+3]) in index order: it sees the samples before i as already
+                // patched, the ones after it raw, so only samples within two of each other depend on one another.
+                // A lane takes a run of such samples (nearly always a single one) from its first sample on.
+                for (int t0 = lane; t0 < ns; t0 += 32) {
+                    if (t0 > 0 && sidx[t0] - sidx[t0 - 1] <= 2u) continue;
+                    int p1i = -8, p2i = -8, p1v = 0, p2v = 0;
+                    for (int t = t0; t < ns && (t == t0 || sidx[t] - sidx[t - 1] <= 2u); ++t) {
+                        const int i = (int)sidx[t];
+                        const int old = sm.spike_w[t][2];
+                        int nv = old;
+                        if (i > 2) {                               // (fast5.py:93: the first three samples are left alone)
+                            const int n = min(5, N - (i - 2));     // 3, 4 or 5 samples; the rest +inf
+                            int v[5];
+#pragma unroll
+                            for (int u = 0; u < 5; ++u) {
+                                const int idx = i - 2 + u;
+                                int vv = sm.spike_w[t][u];
+                                if (idx == p1i) vv = p1v;
+                                else if (idx == p2i) vv = p2v;
+                                v[u] = u < n ? vv : INT_MAX;
+                            }
+#define WSTR_CSWAP(a_, b_)                     \
+    {                                          \
+        const int lo_ = min(v[a_], v[b_]);     \
+        v[b_] = max(v[a_], v[b_]);             \
+        v[a_] = lo_;                           \
+    }
+                            WSTR_CSWAP(0, 1) WSTR_CSWAP(3, 4) WSTR_CSWAP(2, 4) WSTR_CSWAP(2, 3) WSTR_CSWAP(0, 3)
+                            WSTR_CSWAP(0, 2) WSTR_CSWAP(1, 4) WSTR_CSWAP(1, 3) WSTR_CSWAP(1, 2)
+#undef WSTR_CSWAP
+                            // numpy's median; the mean of the middle two is truncated toward zero when stored back
+                            // into the int16 array (fast5.py:100)
+                            nv = n == 5 ? v[2] : n == 4 ? (v[1] + v[2]) / 2 : v[1];
+                            if (nv != old) {                       // from one histogram bin to another
+                                if (old < wlo) atomicAdd(&sm.below, -1);
+                                else if (old >= wlo + WBINS) atomicAdd(&sm.above, -1);
+                                else atomicAdd(&sm.hist[(old - wlo) << 5], 0xffffffffu);   // (a column may wrap, the row sum does not)
+                                if (nv < wlo) atomicAdd(&sm.below, 1);
+                                else if (nv >= wlo + WBINS) atomicAdd(&sm.above, 1);
+                                else atomicAdd(&sm.hist[(nv - wlo) << 5], 1u);
+                            }
+                            p2i = p1i;
+                            p2v = p1v;
+                            p1i = i;
+                            p1v = nv;
                         }
-                        const int16_t nv = median_small(w5, n);
-                        const int16_t old = sm.spike_w[slot][2];
-                        if (nv != old) hist_move(old, nv);
-                        if (i >= lo && i <= hi) stash[i - lo] = nv;
-                        p2i = p1i;
-                        p2v = p1v;
-                        p1i = i;
-                        p1v = nv;
+                        sm.spike_nv[t] = (int16_t)nv;
                     }
                 }
             }
-        } else {
-            scan_tiles();
-        }
-        atomicMin(&sm.vmin, lmin);
-        atomicMax(&sm.vmax, lmax);
-        __threadfence_block();
-        __syncthreads();
-
-        // np.percentile(data, (46.5, 53.5)) (method 'linear'), their mean = shift, np.median(|data - shift|) = scale
-        auto percentile_from = [&](auto &&rank_value, double q) {
-            const double vidx = (double)(N - 1) * q;
-            int64_t i0 = (int64_t)floor(vidx), i1 = i0 + 1;
-            if (vidx >= (double)(N - 1)) i0 = i1 = N - 1;
-            const double gamma = vidx - (double)i0;
-            const int a = rank_value(i0);
-            const int b = rank_value(i1);
-            const int16_t diff16 = (int16_t)(b - a);              // numpy subtracts in int16
-            const double diff = (double)diff16;
-            double res = (double)a + diff * gamma;
-            if (gamma >= 0.5) res = (double)b - diff * (1.0 - gamma);
-            return res;
-        };
-        const bool by_prefix = !sm.ghist_dirty && N > 0;           // block-uniform (set before the barrier above)
-        if (by_prefix) {
-            // in-place inclusive prefix sums of hist[vmin..vmax]: a contiguous run of bins per thread, the
-            // threads' totals scanned through shared memory
-            const int v0 = sm.vmin, R = sm.vmax - sm.vmin + 1;
-            const int per = (R + NT - 1) / NT;
-            const int b0 = v0 + tid * per, b1 = min(b0 + per, v0 + R);
-            uint32_t sum = 0u;
-            for (int b = b0; b < b1; ++b) sum += sm.hist[b];
-            uint32_t inc = sum;
+            __syncthreads();
+        WSTR_NORM_T(3);
+            // the 32 columns of every bin summed (and left zero), then inclusive prefix sums over the bins: three
+            // adjacent bins per thread of the first RED_T; a quarter warp's eight 16-byte accesses cover the 32 banks once
+            constexpr int BPT = 3, RED_T = WBINS / BPT;
+            static_assert(WBINS % BPT == 0 && RED_T % 32 == 0 && RED_T <= NT && WBINS % 32 == 0, "window reduction layout");
+            uint32_t sb[BPT] = {0u, 0u, 0u};
+            if (tid < RED_T) {
+#pragma unroll
+                for (int q = 0; q < BPT; ++q) {
+                    uint4 *row = reinterpret_cast<uint4 *>(sm.hist + ((BPT * tid + q) << 5));
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = (j + tid) & 7;
+                        const uint4 x = row[c];
+                        row[c] = make_uint4(0u, 0u, 0u, 0u);
+                        acc += x.x + x.y + x.z + x.w;
+                    }
+                    sb[q] = acc;
+                }
+            }
+            const uint32_t mine3 = sb[0] + sb[1] + sb[2];
+            uint32_t inc = mine3;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -740,77 +1046,233 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             }
             if (lane == 31) sm.spike_bits[warp] = inc;            // (free between reads; 8 warp totals)
             __syncthreads();
-            uint32_t base = inc - sum;
-            for (int w = 0; w < warp; ++w) base += sm.spike_bits[w];
-            for (int b = b0; b < b1; ++b) {
-                base += sm.hist[b];
-                sm.hist[b] = base;
+            if (tid < RED_T) {
+                uint32_t base = inc - mine3;
+                for (int w = 0; w < warp; ++w) base += sm.spike_bits[w];
+#pragma unroll
+                for (int q = 0; q < BPT; ++q) {
+                    base += sb[q];
+                    cum[BPT * tid + q] = base;
+                }
             }
             __syncthreads();
+        WSTR_NORM_T(4);
             if (tid < TILE / 32) sm.spike_bits[tid] = 0u;         // leave the bitmap clean
-            if (tid == 0) {
-                const double p0 = percentile_from([&](int64_t rk) { return value_at_rank_cum(sm, rk); }, 46.5 / 100.0);
-                const double p1 = percentile_from([&](int64_t rk) { return value_at_rank_cum(sm, rk); }, 53.5 / 100.0);
+            if (warp == 0 && ns <= SPIKE_CAP) {
+                // Order statistics by the whole warp: a monotone predicate over the bins is located with two
+                // ballots (the lanes' block ends, then the block's bins).  Every rank query has to fall inside the
+                // window; one that does not sends the read to the general path below.
+                const int64_t below = sm.below;
+                const int64_t inside = cum[WBINS - 1];
+                bool ok = true;                                   // (warp-uniform throughout)
+                auto wcum = [&](int v) -> int64_t {               // samples <= v, for v in [wlo - 1, wlo + WBINS)
+                    return v < wlo ? below : below + (int64_t)cum[v - wlo];
+                };
+                auto value_at = [&](int64_t rank) -> int {        // smallest v with (samples <= v) > rank
+                    if (rank < below || rank >= below + inside) {
+                        ok = false;
+                        return 0;
+                    }
+                    constexpr int B = WBINS / 32;
+                    const bool e1 = below + (int64_t)cum[lane * B + B - 1] > rank;
+                    const int L = __ffs(__ballot_sync(0xffffffffu, e1)) - 1;
+                    const bool e2 = lane < B && below + (int64_t)cum[L * B + min(lane, B - 1)] > rank;
+                    const int q = __ffs(__ballot_sync(0xffffffffu, e2)) - 1;
+                    return wlo + L * B + q;
+                };
+                const double p0 = percentile_from(value_at, 46.5 / 100.0);
+                const double p1 = percentile_from(value_at, 53.5 / 100.0);
                 const double shift = (p0 + p1) / 2.0;
-                double scale;
+                const int fl = (int)floor(shift);
+                // values by |v - shift|: the pairs (fl - m, fl + 1 + m), m = 0, 1, ...; the first m pairs hold the
+                // samples in [fl - m + 1, fl + m].  m_max: the last pair inside the window
+                const int m_max = ok ? min(fl - wlo, wlo + WBINS - 2 - fl) : -1;
+                auto pairs = [&](int m) -> int64_t { return wcum(fl + m + 1) - wcum(fl - m - 1); };
+                auto absdev_at = [&](int64_t rank) -> double {
+                    if (m_max < 0 || pairs(m_max) <= rank) {
+                        ok = false;
+                        return 0.0;
+                    }
+                    const int B = (m_max + 32) / 32;              // smallest m with pairs(m) > rank
+                    const bool e1 = pairs(min(lane * B + B - 1, m_max)) > rank;
+                    const int L = __ffs(__ballot_sync(0xffffffffu, e1)) - 1;
+                    const int mq = L * B + lane;
+                    const bool e2 = lane < B && mq <= m_max && pairs(min(mq, m_max)) > rank;
+                    const int mm = L * B + __ffs(__ballot_sync(0xffffffffu, e2)) - 1;
+                    const int64_t before = wcum(fl + mm) - wcum(fl - mm);
+                    const int64_t scl = wcum(fl - mm) - wcum(fl - mm - 1);
+                    const int64_t sch = wcum(fl + 1 + mm) - wcum(fl + mm);
+                    const double dl = fabs((double)(fl - mm) - shift), du = fabs((double)(fl + 1 + mm) - shift);
+                    const int64_t within = rank - before;
+                    if (dl <= du) return within < scl ? dl : du;  // inside the pair the nearer value first
+                    return within < sch ? du : dl;
+                };
+                double scale = 0.0;
                 if (N & 1) {
-                    scale = absdev_at_rank_cum(sm, shift, N / 2);
+                    scale = absdev_at(N / 2);
                 } else {
-                    const double m1 = absdev_at_rank_cum(sm, shift, N / 2 - 1);
-                    const double m2 = absdev_at_rank_cum(sm, shift, N / 2);
+                    const double m1 = absdev_at(N / 2 - 1);
+                    const double m2 = absdev_at(N / 2);
                     scale = (m1 + m2) / 2.0;
                 }
-                sm.shift = shift;
-                sm.scale = scale;
-                if (p.shift_scale) {
-                    p.shift_scale[2 * r] = shift;
-                    p.shift_scale[2 * r + 1] = scale;
+                if (ok && lane == 0) {
+                    sm.shift = shift;
+                    sm.scale = scale;
+                    if (p.shift_scale) {
+                        p.shift_scale[2 * r] = shift;
+                        p.shift_scale[2 * r + 1] = scale;
+                    }
+                    sm.win_ok = 1;
                 }
             }
-        } else if (warp == 0 && N > 0) {
-            // samples outside [0, HBINS) went to the global histogram: walk the bins
-            const double p0 = percentile_from([&](int64_t rk) { return value_at_rank(sm, gh, rk, lane); }, 46.5 / 100.0);
-            const double p1 = percentile_from([&](int64_t rk) { return value_at_rank(sm, gh, rk, lane); }, 53.5 / 100.0);
-            const double shift = (p0 + p1) / 2.0;
-            // np.median(np.abs(data - shift))
-            double scale;
-            if (N & 1) {
-                scale = absdev_at_rank(sm, gh, shift, N / 2, lane);
-            } else {
-                const double m1 = absdev_at_rank(sm, gh, shift, N / 2 - 1, lane);
-                const double m2 = absdev_at_rank(sm, gh, shift, N / 2, lane);
-                scale = (m1 + m2) / 2.0;
+            __syncthreads();
+            done = sm.win_ok != 0;
+        }
+
+        // ---- general path: the median filters, and the reads the window did not hold ----------------------
+        if (!done) {
+            for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
+            if (tid == 0) {
+                sm.vmin = 32767;
+                sm.vmax = -32768;
+                sm.n_spikes = 0;
+                sm.old_dirty = 1;
             }
-            if (lane == 0) {
-                sm.shift = shift;
-                sm.scale = scale;
-                if (p.shift_scale) {
-                    p.shift_scale[2 * r] = shift;
-                    p.shift_scale[2 * r + 1] = scale;
+            if (tid < HALO) sm.tile[tid] = 0;
+            if (tid < TILE / 32) sm.spike_bits[tid] = 0u;
+            __syncthreads();
+            if (p.spike_mode <= 1) {
+                scan_fast();
+                __syncthreads();
+                const int ns = sm.n_spikes;
+                if (ns > SPIKE_CAP) {
+                    // too many for the list: start over on the tile path
+                    __syncthreads();
+                    for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
+                    if (sm.ghist_dirty)
+                        for (int b = tid; b < GBINS; b += NT) gh[b] = 0u;
+                    lmin = 32767;
+                    lmax = -32768;
+                    __syncthreads();
+                    if (tid == 0) sm.ghist_dirty = 0;
+                    __syncthreads();
+                    scan_tiles();
+                } else if (ns > 0 && warp == 0) {
+                    patch_spikes(ns, hist_move);
+                }
+            } else {
+                scan_tiles();
+            }
+            atomicMin(&sm.vmin, lmin);
+            atomicMax(&sm.vmax, lmax);
+            __threadfence_block();
+            __syncthreads();
+
+            // np.percentile(data, (46.5, 53.5)), their mean = shift, np.median(|data - shift|) = scale
+            const bool by_prefix = !sm.ghist_dirty && N > 0;           // block-uniform (set before the barrier above)
+            if (by_prefix) {
+                // in-place inclusive prefix sums of hist[vmin..vmax]: a contiguous run of bins per thread, the
+                // threads' totals scanned through shared memory
+                const int v0 = sm.vmin, R = sm.vmax - sm.vmin + 1;
+                const int per = (R + NT - 1) / NT;
+                const int b0 = v0 + tid * per, b1 = min(b0 + per, v0 + R);
+                uint32_t sum = 0u;
+                for (int b = b0; b < b1; ++b) sum += sm.hist[b];
+                uint32_t inc = sum;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) sm.spike_bits[warp] = inc;            // (free between reads; 8 warp totals)
+                __syncthreads();
+                uint32_t base = inc - sum;
+                for (int w = 0; w < warp; ++w) base += sm.spike_bits[w];
+                for (int b = b0; b < b1; ++b) {
+                    base += sm.hist[b];
+                    sm.hist[b] = base;
+                }
+                __syncthreads();
+                if (tid < TILE / 32) sm.spike_bits[tid] = 0u;         // leave the bitmap clean
+                if (tid == 0) {
+                    const double p0 = percentile_from([&](int64_t rk) { return value_at_rank_cum(sm, rk); }, 46.5 / 100.0);
+                    const double p1 = percentile_from([&](int64_t rk) { return value_at_rank_cum(sm, rk); }, 53.5 / 100.0);
+                    const double shift = (p0 + p1) / 2.0;
+                    double scale;
+                    if (N & 1) {
+                        scale = absdev_at_rank_cum(sm, shift, N / 2);
+                    } else {
+                        const double m1 = absdev_at_rank_cum(sm, shift, N / 2 - 1);
+                        const double m2 = absdev_at_rank_cum(sm, shift, N / 2);
+                        scale = (m1 + m2) / 2.0;
+                    }
+                    sm.shift = shift;
+                    sm.scale = scale;
+                    if (p.shift_scale) {
+                        p.shift_scale[2 * r] = shift;
+                        p.shift_scale[2 * r + 1] = scale;
+                    }
+                }
+            } else if (warp == 0 && N > 0) {
+                // samples outside [0, HBINS) went to the global histogram: walk the bins
+                const double p0 = percentile_from([&](int64_t rk) { return value_at_rank(sm, gh, rk, lane); }, 46.5 / 100.0);
+                const double p1 = percentile_from([&](int64_t rk) { return value_at_rank(sm, gh, rk, lane); }, 53.5 / 100.0);
+                const double shift = (p0 + p1) / 2.0;
+                // np.median(np.abs(data - shift))
+                double scale;
+                if (N & 1) {
+                    scale = absdev_at_rank(sm, gh, shift, N / 2, lane);
+                } else {
+                    const double m1 = absdev_at_rank(sm, gh, shift, N / 2 - 1, lane);
+                    const double m2 = absdev_at_rank(sm, gh, shift, N / 2, lane);
+                    scale = (m1 + m2) / 2.0;
+                }
+                if (lane == 0) {
+                    sm.shift = shift;
+                    sm.scale = scale;
+                    if (p.shift_scale) {
+                        p.shift_scale[2 * r] = shift;
+                        p.shift_scale[2 * r + 1] = scale;
+                    }
                 }
             }
         }
         __syncthreads();
+        WSTR_NORM_T(5);
         const double shift = sm.shift, scale = sm.scale;
 
-        // convert the stashed int16 window in place, front to back, one tile at a time
-        for (int64_t t0 = 0; t0 < Tw; t0 += TILE) {
-            const int len = (int)min((int64_t)TILE, Tw - t0);
-            for (int t = tid; t < len; t += NT) sm.tile[HALO + t] = stash[t0 + t];
-            __syncthreads();
-            for (int t = tid; t < len; t += NT) out[t0 + t] = ((double)sm.tile[HALO + t] - shift) / scale;
-            __syncthreads();
+        if (done) {
+            // window path: straight from the read, then the patched samples the window holds
+            for (int t = tid; t < Tw; t += NT) out[t] = ((double)raw[lo + t] - shift) / scale;
+            if (win_ns > 0) {
+                __syncthreads();
+                const uint32_t *const sidx = reinterpret_cast<const uint32_t *>(sm.spike_key);
+                for (int t = tid; t < win_ns; t += NT) {
+                    const int i = (int)sidx[t];
+                    if (i >= lo && i - lo < Tw) out[i - lo] = ((double)sm.spike_nv[t] - shift) / scale;
+                }
+            }
+        } else {
+            // convert the stashed int16 window in place, front to back, one tile at a time
+            for (int64_t t0 = 0; t0 < Tw; t0 += TILE) {
+                const int len = (int)min((int64_t)TILE, Tw - t0);
+                for (int t = tid; t < len; t += NT) sm.tile[HALO + t] = stash[t0 + t];
+                __syncthreads();
+                for (int t = tid; t < len; t += NT) out[t0 + t] = ((double)sm.tile[HALO + t] - shift) / scale;
+                __syncthreads();
+            }
         }
         // leave the global fallback histogram clean for the next read
         if (sm.ghist_dirty) {
             for (int b = tid; b < GBINS; b += NT) gh[b] = 0u;
         }
         __syncthreads();
+        WSTR_NORM_T(6);
     }
 }
 
 int norm_grid(int n_reads) {
-    int g = 148 * WSTR_NORM_BLOCKS;   // persistent: one CTA per resident slot (48 registers, 37 KB of shared memory each)
+    int g = 148 * WSTR_NORM_BLOCKS;   // persistent: one CTA per resident slot
     return n_reads < g ? (n_reads < 1 ? 1 : n_reads) : g;
 }
 
