@@ -249,8 +249,13 @@ struct NormSmem {
     int16_t spike_w[SPIKE_CAP][5];
     int16_t spike_nv[SPIKE_CAP];     // window path: the samples' values after patching
     int32_t n_spikes;
-    int32_t next_read;
-    int32_t wlo, below, above;       // window path: first value of the window, samples under / over it
+    // the read being worked on and the next one, prepared by the last warp while warp 0 patches and ranks:
+    // its queue slot, offsets, window, and (Brute / None) where its histogram window goes
+    struct Meta {
+        int64_t raw_off, out_off;
+        int32_t r, N, lo, hi, wlo;
+    } meta[2];
+    int32_t below, above;            // window path: samples under / over the window
     int32_t win_ok, old_dirty;
     int32_t vmin, vmax;
     int32_t ghist_dirty;
@@ -534,21 +539,64 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
 
     long long t_phase_ = 0;
     (void)t_phase_;
-    for (;;) {
-        if (tid == 0) sm.next_read = atomicAdd(p.queue, 1);
-        __syncthreads();
-        const int r = sm.next_read;
+    const bool try_window = p.spike_mode <= 1;
+    // (last warp) the read in queue slot `slot` into meta[which]: offsets, window and -- for the window path --
+    // the median of 32 samples spread over the read (each lane ranks its own), WBINS / 2 under which the
+    // histogram window starts
+    auto prepare = [&](int slot, int which) {
+        NormSmem::Meta &m = sm.meta[which];
+        if (lane == 0) m.r = slot;
+        if (slot >= p.n_reads) return;
+        const int64_t ro = p.raw_off[slot];
+        // (a read has fewer than 2^31 - 2*TILE samples, checked by the host: tile-relative indices fit an int)
+        const int n = (int)(p.raw_off[slot + 1] - ro);
+        if (lane == 0) {
+            m.raw_off = ro;
+            m.out_off = p.out_off[slot];
+            m.N = n;
+            m.lo = p.win_lo[slot];
+            m.hi = p.win_hi[slot];
+        }
+        if (try_window) {
+            const int mine = p.raw[ro + (((int64_t)lane * n) >> 5)];
+            int rank = 0;
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                const int other = __shfl_sync(0xffffffffu, mine, o);
+                rank += (other < mine || (other == mine && o < lane)) ? 1 : 0;
+            }
+            if (rank == 16) m.wlo = mine - WBINS / 2;
+        }
+    };
+    constexpr int PREP_WARP = NT / 32 - 1;
+    if (warp == PREP_WARP) {
+        int slot = lane == 0 ? atomicAdd(p.queue, 1) : 0;
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        prepare(slot, 0);
+    }
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const NormSmem::Meta &meta = sm.meta[it & 1];
+        const int r = meta.r;
         WSTR_NORM_T(0);
         if (r >= p.n_reads) break;
-        const int16_t *raw = p.raw + p.raw_off[r];
-        // (a read has fewer than 2^31 - 2*TILE samples, checked by the host: tile-relative indices fit an int)
-        const int N = (int)(p.raw_off[r + 1] - p.raw_off[r]);
-        const int lo = p.win_lo[r], hi = p.win_hi[r];
+        // the next read's queue slot: asked for now, looked at after the scan
+        int next_slot = (tid == PREP_WARP * 32) ? atomicAdd(p.queue, 1) : 0;
+        bool prepared = false;
+        auto prepare_next = [&]() {                                  // (all of the last warp, once per read)
+            if (warp == PREP_WARP && !prepared) {
+                next_slot = __shfl_sync(0xffffffffu, next_slot, 0);
+                prepare(next_slot, (it + 1) & 1);
+                prepared = true;
+            }
+        };
+        const int16_t *raw = p.raw + meta.raw_off;
+        const int N = meta.N;
+        const int lo = meta.lo, hi = meta.hi;
         const int Tw = hi >= lo ? max(min(hi, N - 1) - lo + 1, 0) : 0;   // numpy slice semantics
-        double *out = p.out + p.out_off[r];
+        double *out = p.out + meta.out_off;
         int16_t *stash = reinterpret_cast<int16_t *>(out) + 3 * (int64_t)Tw;   // tail of the output window
 
-        const bool try_window = p.spike_mode <= 1;
         if (try_window && sm.old_dirty)                                  // (block-uniform: written before a barrier)
             for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
         if (tid == 0) {
@@ -618,11 +666,9 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                 if (d < n_tiles) issue(d, jstep + d);
         };
         auto scan_window = [&]() {
-            const int wlo = sm.wlo;
+            const int wlo = meta.wlo;
             ctx.wlo = wlo;
             uint32_t *const col = sm.hist + lane - wlo * 32;     // col[v * 32] = this lane's counter of value v
-            const int ok_lo = p.spike_mode == 1 ? max(wlo, 250) : wlo;
-            const int ok_hi = p.spike_mode == 1 ? min(wlo + WBINS - 1, 1000) : wlo + WBINS - 1;
             for (int k = 0; k < n_tiles; ++k) {
                 const uint32_t j = jstep + k, st = j % NSTAGE, use = j / NSTAGE;
                 while (!nbar_try_wait(&sm.full[st], use & 1u)) {
@@ -641,25 +687,30 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                 const unsigned mx = __vmaxs2(__vmaxs2(cur.q.x, cur.q.y), __vmaxs2(cur.q.z, cur.q.w));
                 const int tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
                 const int tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
-#if WSTR_NORM_EXP == 8
                 if (plain) {
-                    n_below += tmin + tmax;
-                    continue;
-                }
-#elif WSTR_NORM_EXP == 9
-                n_below += tmin + tmax;
-                continue;
-#endif
-                if (plain && tmin >= ok_lo && tmax <= ok_hi) {
+                    if (tmin >= wlo && tmax <= wlo + WBINS - 1) {
 #pragma unroll
-#if WSTR_NORM_EXP == 1
-                    for (int u = 0; u < PER; ++u) atomicAdd(sm.hist + ((int)cur.h[u] - wlo), 1u);
-#elif WSTR_NORM_EXP == 2
-                    for (int u = 0; u < PER; ++u) n_below += cur.h[u] == 12345;
-#else
-                    for (int u = 0; u < PER; ++u) atomicAdd(col + (int)cur.h[u] * 32, 1u);
-#endif
-                } else {
+                        for (int u = 0; u < PER; ++u) atomicAdd(col + (int)cur.h[u] * 32, 1u);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < PER; ++u) {
+                            const int vv = cur.h[u];
+                            if ((unsigned)(vv - wlo) < (unsigned)WBINS) atomicAdd(col + vv * 32, 1u);
+                            else if (vv < wlo) ++n_below;
+                            else ++n_above;
+                        }
+                    }
+                    if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {   // note where Brute will patch
+                        const int g0 = t_base + tid * PER;
+#pragma unroll
+                        for (int u = 0; u < PER; ++u) {
+                            if (cur.h[u] > 1000 || cur.h[u] < 250) {
+                                const int pos = atomicAdd(&sm.n_spikes, 1);
+                                if (pos < SPIKE_CAP) reinterpret_cast<uint32_t *>(sm.spike_key)[pos] = (uint32_t)(g0 + u);
+                            }
+                        }
+                    }
+                } else {                                           // a tile that hangs over an end of the read
                     const int ba = norm_step_general<true>(sm, ctx, cur.q, k);
                     n_below += ba & 0xff;
                     n_above += ba >> 8;
@@ -902,21 +953,10 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         // ---- window path (Brute / None) -------------------------------------------------------------------
         bool done = false;
         int win_ns = 0;
+        constexpr int WREG = 8;                                   // output windows up to 4096 samples are held in registers
+        uint32_t wreg[WREG];
         if (try_window) {
-            // where the window goes: the median of 32 samples spread over the read (warp 0, each lane ranks
-            // its own sample), WBINS / 2 under it
             if (tid == 0) scan_window_prologue();
-            if (warp == 0) {
-                const int mine = raw[(int)(((int64_t)lane * N) >> 5)];
-                int rank = 0;
-#pragma unroll
-                for (int o = 0; o < 32; ++o) {
-                    const int other = __shfl_sync(0xffffffffu, mine, o);
-                    rank += (other < mine || (other == mine && o < lane)) ? 1 : 0;
-                }
-                if (rank == 16) sm.wlo = mine - WBINS / 2;
-            }
-            __syncthreads();
         WSTR_NORM_T(1);
             scan_window();
 #pragma unroll
@@ -930,15 +970,40 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             }
             __syncthreads();
         WSTR_NORM_T(2);
-            const int wlo = sm.wlo;
+            const int wlo = meta.wlo;
             const int ns = sm.n_spikes;
             win_ns = ns;
+            // the output window's samples, two per register, asked for now and used after the statistics
+            if (Tw <= NT * 2 * WREG) {
+#pragma unroll
+                for (int i = 0; i < WREG; ++i) {
+                    const int t0 = tid + (2 * i) * NT, t1 = t0 + NT;
+                    const uint32_t a = t0 < Tw ? (uint16_t)raw[lo + t0] : 0u;
+                    const uint32_t b2 = t1 < Tw ? (uint16_t)raw[lo + t1] : 0u;
+                    wreg[i] = a | b2 << 16;
+                }
+            }
+            prepare_next();                                       // (the last warp; warp 0 has the patching and the statistics to do)
             uint32_t *const sidx = reinterpret_cast<uint32_t *>(sm.spike_key);   // the noted samples' indices
             if (ns > 0 && ns <= SPIKE_CAP && warp == 0) {
                 // Brute (fast5.py:90-101) on the noted samples.  Ascending order (bitonic network, +inf beyond ns) ...
+                if (ns <= 32) {                                    // one index per lane, sorted across the warp
+                    uint32_t key = lane < ns ? sidx[lane] : 0xffffffffu;
+#pragma unroll
+                    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                        for (int j = kk >> 1; j > 0; j >>= 1) {
+                            const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+                            const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                            key = (lower == up) ? min(key, other) : max(key, other);
+                        }
+                    }
+                    if (lane < ns) sidx[lane] = key;
+                    __syncwarp();
+                }
                 int P = 1;
                 while (P < ns) P <<= 1;
-                for (int kk = 2; kk <= P; kk <<= 1) {
+                for (int kk = 2; kk <= P && ns > 32; kk <<= 1) {
                     for (int j = kk >> 1; j > 0; j >>= 1) {
                         const int flip = j == (kk >> 1) ? kk - 1 : j;
                         for (int t = lane; t < (P >> 1); t += 32) {
@@ -1237,13 +1302,25 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                 }
             }
         }
+        prepare_next();
         __syncthreads();
         WSTR_NORM_T(5);
         const double shift = sm.shift, scale = sm.scale;
 
         if (done) {
             // window path: straight from the read, then the patched samples the window holds
-            for (int t = tid; t < Tw; t += NT) out[t] = ((double)raw[lo + t] - shift) / scale;
+            if (Tw <= NT * 2 * WREG) {
+#pragma unroll
+                for (int i = 0; i < WREG; ++i) {                 // (the quotients unconditionally: independent chains)
+                    const int t0 = tid + (2 * i) * NT, t1 = t0 + NT;
+                    const double q0 = ((double)(int16_t)(wreg[i] & 0xffffu) - shift) / scale;
+                    const double q1 = ((double)(int16_t)(wreg[i] >> 16) - shift) / scale;
+                    if (t0 < Tw) out[t0] = q0;
+                    if (t1 < Tw) out[t1] = q1;
+                }
+            } else {
+                for (int t = tid; t < Tw; t += NT) out[t] = ((double)raw[lo + t] - shift) / scale;
+            }
             if (win_ns > 0) {
                 __syncthreads();
                 const uint32_t *const sidx = reinterpret_cast<const uint32_t *>(sm.spike_key);
