@@ -133,6 +133,8 @@ def test_normalisation_window_histogram_and_its_fallback(built_lib, mode):
     for i, r in enumerate(raws):
         if i % 2 == 0 and len(r) > 100:
             r[rng.integers(3, len(r), max(len(r) // 3000, 3))] = rng.choice([1500, 90, 30000])
+    raws.append(np.full(2_200_000, 480, dtype=np.int16))                                 # too long for the 16-bit counters
+    raws.append(np.full(2_090_000, 481, dtype=np.int16))                                 # ... and nearly: one bin takes it all
     r = (470 + 28 * rng.standard_normal(30000)).astype(np.int16)                        # more spikes than the list holds
     r[rng.integers(3, len(r), 600)] = 1400
     raws.append(r)

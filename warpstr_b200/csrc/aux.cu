@@ -207,12 +207,15 @@ constexpr int NT = 256;              // threads per CTA
 constexpr int PER = 8;               // samples per thread per tile
 constexpr int TILE = NT * PER;       // 2048
 constexpr int HBINS = 8192;          // shared histogram (general path) covers values [0, HBINS)
-constexpr int WBINS = 384;           // window histogram (Brute / None): values [wlo, wlo + WBINS), one column per lane
+constexpr int WBINS = 512;           // window histogram (Brute / None): values [wlo, wlo + WBINS), one column per lane
 constexpr int GBINS = 65536;         // global fallback histogram covers every int16
 #ifndef WSTR_NORM_DEPTH
-#define WSTR_NORM_DEPTH 4            // tiles in flight per CTA
+#define WSTR_NORM_DEPTH 3            // stages in flight per CTA
 #endif
-constexpr int NSTAGE = WSTR_NORM_DEPTH + 1;   // tiles of shared memory the window scan's bulk copies rotate through
+constexpr int NSTAGE = WSTR_NORM_DEPTH + 1;   // stages of shared memory the window scan's bulk copies rotate through
+constexpr int WSTEP = 2;                      // tiles per stage (one wait and one release per WSTEP tiles)
+constexpr int WCOLS = 16;                     // words per bin of the window histogram: a 16-bit counter per lane
+constexpr int WIN_MAX_N = (65535 - 64) * 32;  // longest read whose per-lane counts cannot overflow them
 constexpr int SPIKE_CAP = 256;       // out-of-range samples of one read the barrier-free path can hold
 
 struct NormParams {
@@ -229,16 +232,18 @@ struct NormParams {
 };
 
 struct NormSmem {
-    // general path: hist[v], v in [0, HBINS).  Window path: hist[(v - wlo) * 32 + lane] -- every lane of a
-    // warp counts into its own bank, so the eight increments a thread issues per step never meet a bank
-    // conflict (a value-indexed histogram costs ~3.5 replays per warp instruction on random values).
-    alignas(16) uint32_t hist[WBINS * 32];
+    // general path: hist[v], v in [0, HBINS).  Window path: a 16-bit counter per bin and lane, hist[(v - wlo) *
+    // WCOLS + lane / 2], halves by lane parity: no two lanes of a warp ever meet in a bank at different words.
+    // corr[bin]: the samples Brute moved into (+) or out of (-) a bin, kept apart because a counter must not
+    // borrow from its neighbour.
+    alignas(16) uint32_t hist[WBINS * WCOLS];
+    int32_t corr[WBINS];
     // Window path: NSTAGE tiles of raw samples, filled by bulk asynchronous copies (one thread issues,
     // every thread reads its eight samples back with one 16-byte load).  Tile path and the final
     // conversion: tile[HALO + t] = sample t of the current tile; tile[HALO-2], tile[HALO-1] = the two
     // (patched) samples before it.  HALO = 8 keeps the tile 16-byte aligned for vector access.
     union {
-        alignas(128) int16_t stage[NSTAGE * TILE];
+        alignas(128) int16_t stage[NSTAGE * WSTEP * TILE];
         alignas(16) int16_t tile[TILE + 16];
     };
     alignas(8) uint64_t full[NSTAGE], empty[NSTAGE];
@@ -422,20 +427,18 @@ struct NormCtx {
 
 // One thread's eight samples of tile k of the barrier-free scan, no assumption made: the tile may hang over either
 // end of the read or meet the output window, samples may be Brute's to patch (noted in the spike list with their
-// neighbourhoods) or lie outside the histogram.  WIN: the lane-column window histogram, returns (samples under the
+// neighbourhoods) or lie outside the histogram.  WIN: the per-lane window histogram, returns (samples under the
 // window) | (samples over it) << 8; otherwise the value-indexed histogram with the global one behind it, returns
 // (min & 0xffff) | max << 16 of the valid samples.
 template <bool WIN>
-__device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, const uint4 loaded, const int k) {
+__device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, const uint4 loaded, const int g0) {
     union {
         uint4 q;
         int16_t h[PER];
     } cur;
-    cur.q = loaded;
+    cur.q = loaded;                                               // samples g0 .. g0 + 7 of the read
     const int N = c.N, lo = c.lo, hi = c.hi, wlo = c.wlo;
-    const int t_base = k * TILE - c.mis;
-    const int g0 = t_base + c.tid * PER;
-    const bool in_window = t_base <= hi && t_base + TILE > lo;
+    const bool in_window = g0 <= hi && g0 + PER > lo;
     int tmin = 32767, tmax = -32768;
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
@@ -468,7 +471,8 @@ __device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, co
     }
     int ret;
     if (WIN) {
-        uint32_t *const col = sm.hist + (c.tid & 31) - wlo * 32;
+        uint32_t *const col = sm.hist + ((c.tid & 31) >> 1) - wlo * WCOLS;
+        const uint32_t one = 1u << ((c.tid & 1) * 16);
         int below = 0, above = 0;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
@@ -477,7 +481,7 @@ __device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, co
             const int vv = cur.h[u];
             if (vv < wlo) ++below;
             else if (vv >= wlo + WBINS) ++above;
-            else atomicAdd(col + vv * 32, 1u);
+            else atomicAdd(col + vv * WCOLS, one);
         }
         ret = below | above << 8;
     } else {
@@ -526,7 +530,8 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
     uint32_t *const cum = reinterpret_cast<uint32_t *>(sm.tile);   // window path: prefix sums of the window's bins
 
     // the window path finds its histogram zero and leaves it zero
-    for (int b = tid; b < WBINS * 32; b += NT) sm.hist[b] = 0u;
+    for (int b = tid; b < WBINS * WCOLS; b += NT) sm.hist[b] = 0u;
+    for (int b = tid; b < WBINS; b += NT) sm.corr[b] = 0;
     if (tid == 0) {
         sm.old_dirty = 0;
         for (int b = 0; b < NSTAGE; ++b) {
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
 
     long long t_phase_ = 0;
     (void)t_phase_;
-    const bool try_window = p.spike_mode <= 1;
+    const bool mode_window = p.spike_mode <= 1;
     // (last warp) the read in queue slot `slot` into meta[which]: offsets, window and -- for the window path --
     // the median of 32 samples spread over the read (each lane ranks its own), WBINS / 2 under which the
     // histogram window starts
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             m.lo = p.win_lo[slot];
             m.hi = p.win_hi[slot];
         }
-        if (try_window) {
+        if (mode_window) {
             const int mine = p.raw[ro + (((int64_t)lane * n) >> 5)];
             int rank = 0;
 #pragma unroll
@@ -597,6 +602,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         double *out = p.out + meta.out_off;
         int16_t *stash = reinterpret_cast<int16_t *>(out) + 3 * (int64_t)Tw;   // tail of the output window
 
+        const bool try_window = mode_window && N <= WIN_MAX_N;
         if (try_window && sm.old_dirty)                                  // (block-uniform: written before a barrier)
             for (int b = tid; b < HBINS; b += NT) sm.hist[b] = 0u;
         if (tid == 0) {
@@ -651,72 +657,82 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         // not meeting the output window: min/max two samples per instruction, eight increments -- and is kept
         // that small on purpose; everything else is one out-of-line call.
         // tile k of this read is step j of the kernel: stage j % NSTAGE, its (j / NSTAGE)-th use
-        auto issue = [&](int k, uint32_t j) {                     // (thread 0)
+        const int n_steps = (n_tiles + WSTEP - 1) / WSTEP;       // a stage holds WSTEP tiles
+        auto issue = [&](int k, uint32_t j) {                     // (thread 0) step k of this read
             const uint32_t st = j % NSTAGE, use = j / NSTAGE;
             if (use > 0)
                 while (!nbar_try_wait(&sm.empty[st], (use - 1) & 1u)) {
                 }
-            const int bytes = min(TILE * 2, n_vec * 16 - k * (TILE * 2));
-            nbulk_load(&sm.stage[st * TILE], reinterpret_cast<const char *>(vec) + (size_t)k * (TILE * 2),
+            constexpr int SBYTES = WSTEP * TILE * 2;
+            const int bytes = min(SBYTES, n_vec * 16 - k * SBYTES);
+            nbulk_load(&sm.stage[st * (WSTEP * TILE)], reinterpret_cast<const char *>(vec) + (size_t)k * SBYTES,
                        (uint32_t)bytes, &sm.full[st]);
         };
-        auto scan_window_prologue = [&]() {                       // (thread 0; the copies overlap the estimate below)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was last written by threads
+        auto scan_window_prologue = [&]() {                       // (thread 0)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stages were last written by threads
             for (int d = 0; d < NSTAGE - 1; ++d)
-                if (d < n_tiles) issue(d, jstep + d);
+                if (d < n_steps) issue(d, jstep + d);
         };
         auto scan_window = [&]() {
             const int wlo = meta.wlo;
             ctx.wlo = wlo;
-            uint32_t *const col = sm.hist + lane - wlo * 32;     // col[v * 32] = this lane's counter of value v
-            for (int k = 0; k < n_tiles; ++k) {
+            // col[v * WCOLS] = the word this lane's 16-bit counter of value v lives in, `one` its unit
+            uint32_t *const col = sm.hist + (lane >> 1) - wlo * WCOLS;
+            const uint32_t one = 1u << ((lane & 1) * 16);
+            for (int k = 0; k < n_steps; ++k) {
                 const uint32_t j = jstep + k, st = j % NSTAGE, use = j / NSTAGE;
                 while (!nbar_try_wait(&sm.full[st], use & 1u)) {
                 }
                 union {
                     uint4 q;
                     int16_t h[PER];
-                } cur;
-                cur.q = *reinterpret_cast<const uint4 *>(&sm.stage[st * TILE + tid * PER]);
+                } cur[WSTEP];
+#pragma unroll
+                for (int w = 0; w < WSTEP; ++w)
+                    cur[w].q = *reinterpret_cast<const uint4 *>(&sm.stage[(st * WSTEP + w) * TILE + tid * PER]);
                 nbar_arrive(&sm.empty[st]);
-                // the stage tile k - 1 was in goes to tile k - 1 + NSTAGE (everybody has to have read it: most have)
-                if (tid == 0 && k + NSTAGE - 1 < n_tiles) issue(k + NSTAGE - 1, j + NSTAGE - 1);
-                const int t_base = k * TILE - mis;
-                const bool plain = t_base >= 0 && t_base + TILE <= N;
-                const unsigned mn = __vmins2(__vmins2(cur.q.x, cur.q.y), __vmins2(cur.q.z, cur.q.w));
-                const unsigned mx = __vmaxs2(__vmaxs2(cur.q.x, cur.q.y), __vmaxs2(cur.q.z, cur.q.w));
-                const int tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
-                const int tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
-                if (plain) {
-                    if (tmin >= wlo && tmax <= wlo + WBINS - 1) {
+                // the stage step k - 1 was in goes to step k - 1 + NSTAGE (everybody has to have read it: most have)
+                if (tid == 0 && k + NSTAGE - 1 < n_steps) issue(k + NSTAGE - 1, j + NSTAGE - 1);
 #pragma unroll
-                        for (int u = 0; u < PER; ++u) atomicAdd(col + (int)cur.h[u] * 32, 1u);
-                    } else {
+                for (int w = 0; w < WSTEP; ++w) {
+                    const int t_base = (k * WSTEP + w) * TILE - mis;
+                    if (t_base >= N) continue;                     // (the stage's second tile lies beyond the read)
+                    const uint4 q = cur[w].q;
+                    const unsigned mn = __vmins2(__vmins2(q.x, q.y), __vmins2(q.z, q.w));
+                    const unsigned mx = __vmaxs2(__vmaxs2(q.x, q.y), __vmaxs2(q.z, q.w));
+                    const int tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
+                    const int tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
+                    if (t_base >= 0 && t_base + TILE <= N) {
+                        if (tmin >= wlo && tmax <= wlo + WBINS - 1) {
 #pragma unroll
-                        for (int u = 0; u < PER; ++u) {
-                            const int vv = cur.h[u];
-                            if ((unsigned)(vv - wlo) < (unsigned)WBINS) atomicAdd(col + vv * 32, 1u);
-                            else if (vv < wlo) ++n_below;
-                            else ++n_above;
-                        }
-                    }
-                    if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {   // note where Brute will patch
-                        const int g0 = t_base + tid * PER;
+                            for (int u = 0; u < PER; ++u) atomicAdd(col + (int)cur[w].h[u] * WCOLS, one);
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < PER; ++u) {
-                            if (cur.h[u] > 1000 || cur.h[u] < 250) {
-                                const int pos = atomicAdd(&sm.n_spikes, 1);
-                                if (pos < SPIKE_CAP) reinterpret_cast<uint32_t *>(sm.spike_key)[pos] = (uint32_t)(g0 + u);
+                            for (int u = 0; u < PER; ++u) {
+                                const int vv = cur[w].h[u];
+                                if ((unsigned)(vv - wlo) < (unsigned)WBINS) atomicAdd(col + vv * WCOLS, one);
+                                else if (vv < wlo) ++n_below;
+                                else ++n_above;
                             }
                         }
+                        if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {   // note where Brute will patch
+                            const int g0 = t_base + tid * PER;
+#pragma unroll
+                            for (int u = 0; u < PER; ++u) {
+                                if (cur[w].h[u] > 1000 || cur[w].h[u] < 250) {
+                                    const int pos = atomicAdd(&sm.n_spikes, 1);
+                                    if (pos < SPIKE_CAP) reinterpret_cast<uint32_t *>(sm.spike_key)[pos] = (uint32_t)(g0 + u);
+                                }
+                            }
+                        }
+                    } else {                                       // a tile that hangs over an end of the read
+                        const int ba = norm_step_general<true>(sm, ctx, q, t_base + tid * PER);
+                        n_below += ba & 0xff;
+                        n_above += ba >> 8;
                     }
-                } else {                                           // a tile that hangs over an end of the read
-                    const int ba = norm_step_general<true>(sm, ctx, cur.q, k);
-                    n_below += ba & 0xff;
-                    n_above += ba >> 8;
                 }
             }
-            jstep += (uint32_t)n_tiles;
+            jstep += (uint32_t)n_steps;
         };
         // Value-indexed form (the reads the window did not hold): every step out of line.
         auto scan_fast = [&]() {
@@ -724,7 +740,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             for (int k = 0; k < n_tiles; ++k) {
                 const uint4 q = nxt;
                 nxt = fetch(k + 1);
-                const int mm = norm_step_general<false>(sm, ctx, q, k);
+                const int mm = norm_step_general<false>(sm, ctx, q, k * TILE - mis + tid * PER);
                 lmin = min(lmin, (int)(int16_t)(mm & 0xffff));
                 lmax = max(lmax, mm >> 16);
             }
@@ -1066,10 +1082,10 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                             if (nv != old) {                       // from one histogram bin to another
                                 if (old < wlo) atomicAdd(&sm.below, -1);
                                 else if (old >= wlo + WBINS) atomicAdd(&sm.above, -1);
-                                else atomicAdd(&sm.hist[(old - wlo) << 5], 0xffffffffu);   // (a column may wrap, the row sum does not)
+                                else atomicAdd(&sm.corr[old - wlo], -1);
                                 if (nv < wlo) atomicAdd(&sm.below, 1);
                                 else if (nv >= wlo + WBINS) atomicAdd(&sm.above, 1);
-                                else atomicAdd(&sm.hist[(nv - wlo) << 5], 1u);
+                                else atomicAdd(&sm.corr[nv - wlo], 1);
                             }
                             p2i = p1i;
                             p2v = p1v;
@@ -1082,43 +1098,50 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             }
             __syncthreads();
         WSTR_NORM_T(3);
-            // the 32 columns of every bin summed (and left zero), then inclusive prefix sums over the bins: three
-            // adjacent bins per thread of the first RED_T; a quarter warp's eight 16-byte accesses cover the 32 banks once
-            constexpr int BPT = 3, RED_T = WBINS / BPT;
-            static_assert(WBINS % BPT == 0 && RED_T % 32 == 0 && RED_T <= NT && WBINS % 32 == 0, "window reduction layout");
-            uint32_t sb[BPT] = {0u, 0u, 0u};
-            if (tid < RED_T) {
+            // Every bin's 32 counters (and Brute's corrections) summed and left zero, then inclusive prefix sums over
+            // the bins.  Thread t takes bins t and t + NT: neighbouring threads' rows start 16 banks apart, and with
+            // the 16-byte pieces taken in an order skewed by t / 2 a quarter warp's eight accesses cover the 32 banks once.
+            static_assert(WBINS == 2 * NT && WCOLS == 16, "window reduction layout");
+            uint32_t sb[2];
 #pragma unroll
-                for (int q = 0; q < BPT; ++q) {
-                    uint4 *row = reinterpret_cast<uint4 *>(sm.hist + ((BPT * tid + q) << 5));
-                    uint32_t acc = 0u;
+            for (int q = 0; q < 2; ++q) {
+                const int bin = tid + q * NT;
+                uint4 *row = reinterpret_cast<uint4 *>(sm.hist + bin * WCOLS);
+                uint32_t acc = (uint32_t)sm.corr[bin];
+                sm.corr[bin] = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = (j + tid) & 7;
-                        const uint4 x = row[c];
-                        row[c] = make_uint4(0u, 0u, 0u, 0u);
-                        acc += x.x + x.y + x.z + x.w;
-                    }
-                    sb[q] = acc;
+                for (int j = 0; j < 4; ++j) {
+                    const int c = (j + (tid >> 1)) & 3;
+                    const uint4 x = row[c];
+                    row[c] = make_uint4(0u, 0u, 0u, 0u);
+                    acc += (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) +
+                           (x.w & 0xffffu) + (x.w >> 16);
                 }
+                sb[q] = acc;
             }
-            const uint32_t mine3 = sb[0] + sb[1] + sb[2];
-            uint32_t inc = mine3;
+            uint32_t inc0 = sb[0], inc1 = sb[1];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) sm.spike_bits[warp] = inc;            // (free between reads; 8 warp totals)
-            __syncthreads();
-            if (tid < RED_T) {
-                uint32_t base = inc - mine3;
-                for (int w = 0; w < warp; ++w) base += sm.spike_bits[w];
-#pragma unroll
-                for (int q = 0; q < BPT; ++q) {
-                    base += sb[q];
-                    cum[BPT * tid + q] = base;
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
+                if (lane >= o) {
+                    inc0 += t0;
+                    inc1 += t1;
                 }
+            }
+            if (lane == 31) {                                     // (the bitmap is free between reads: 2 x 8 warp totals)
+                sm.spike_bits[warp] = inc0;
+                sm.spike_bits[8 + warp] = inc1;
+            }
+            __syncthreads();
+            {
+                uint32_t base0 = inc0, base1 = inc1;
+                for (int w = 0; w < NT / 32; ++w) {
+                    if (w < warp) base0 += sm.spike_bits[w];
+                    base1 += sm.spike_bits[w];                    // all of the first half comes before the second
+                    if (w < warp) base1 += sm.spike_bits[8 + w];
+                }
+                cum[tid] = base0;
+                cum[NT + tid] = base1;
             }
             __syncthreads();
         WSTR_NORM_T(4);
