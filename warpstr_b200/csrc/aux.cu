@@ -246,7 +246,8 @@ struct NormSmem {
         alignas(128) int16_t stage[NSTAGE * WSTEP * TILE];
         alignas(16) int16_t tile[TILE + 16];
     };
-    alignas(8) uint64_t full[NSTAGE], empty[NSTAGE];
+    alignas(8) uint64_t full[NSTAGE];
+    uint32_t readers[NSTAGE];        // warps that have taken their samples out of a stage
     uint32_t spike_bits[TILE / 32];  // Brute, tile path: out-of-range samples of the current tile (all zero between tiles)
     // Brute, barrier-free path: the out-of-range samples of the read, (index << 32 | slot) for sorting, and
     // the raw samples i-2 .. i+2 around each, fetched by the thread that found it
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         sm.old_dirty = 0;
         for (int b = 0; b < NSTAGE; ++b) {
             nbar_init(&sm.full[b], 1);
-            nbar_init(&sm.empty[b], NT);
+            sm.readers[b] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -658,27 +659,26 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         // that small on purpose; everything else is one out-of-line call.
         // tile k of this read is step j of the kernel: stage j % NSTAGE, its (j / NSTAGE)-th use
         const int n_steps = (n_tiles + WSTEP - 1) / WSTEP;       // a stage holds WSTEP tiles
-        auto issue = [&](int k, uint32_t j) {                     // (thread 0) step k of this read
-            const uint32_t st = j % NSTAGE, use = j / NSTAGE;
-            if (use > 0)
-                while (!nbar_try_wait(&sm.empty[st], (use - 1) & 1u)) {
-                }
+        auto issue = [&](int k, uint32_t st) {                    // (one thread) step k of this read into stage st
             constexpr int SBYTES = WSTEP * TILE * 2;
             const int bytes = min(SBYTES, n_vec * 16 - k * SBYTES);
             nbulk_load(&sm.stage[st * (WSTEP * TILE)], reinterpret_cast<const char *>(vec) + (size_t)k * SBYTES,
                        (uint32_t)bytes, &sm.full[st]);
         };
-        auto scan_window_prologue = [&]() {                       // (thread 0)
+        auto scan_window_prologue = [&]() {                       // (thread 0; every stage is free between reads)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stages were last written by threads
-            for (int d = 0; d < NSTAGE - 1; ++d)
-                if (d < n_steps) issue(d, jstep + d);
+            for (int d = 0; d < NSTAGE; ++d)
+                if (d < n_steps) issue(d, (jstep + d) % NSTAGE);
         };
         auto scan_window = [&]() {
             const int wlo = meta.wlo;
             ctx.wlo = wlo;
-            // col[v * WCOLS] = the word this lane's 16-bit counter of value v lives in, `one` its unit
-            uint32_t *const col = sm.hist + (lane >> 1) - wlo * WCOLS;
+            // the word this lane's 16-bit counter of value v lives in is at col + v * (4 * WCOLS), `one` its unit
+            const uint32_t col = nsmem_u32(sm.hist + (lane >> 1)) - (uint32_t)(wlo * (4 * WCOLS));
             const uint32_t one = 1u << ((lane & 1) * 16);
+            // all eight samples inside the window and none of them Brute's to patch: the common step
+            const int ok_lo = p.spike_mode == 1 ? max(wlo, 250) : wlo;
+            const int ok_hi = p.spike_mode == 1 ? min(wlo + WBINS - 1, 1000) : wlo + WBINS - 1;
             for (int k = 0; k < n_steps; ++k) {
                 const uint32_t j = jstep + k, st = j % NSTAGE, use = j / NSTAGE;
                 while (!nbar_try_wait(&sm.full[st], use & 1u)) {
@@ -690,9 +690,16 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
 #pragma unroll
                 for (int w = 0; w < WSTEP; ++w)
                     cur[w].q = *reinterpret_cast<const uint4 *>(&sm.stage[(st * WSTEP + w) * TILE + tid * PER]);
-                nbar_arrive(&sm.empty[st]);
-                // the stage step k - 1 was in goes to step k - 1 + NSTAGE (everybody has to have read it: most have)
-                if (tid == 0 && k + NSTAGE - 1 < n_steps) issue(k + NSTAGE - 1, j + NSTAGE - 1);
+                // The last warp to have its samples in registers sends the stage off for step k + NSTAGE: no stage
+                // waits for a particular thread to come by, NSTAGE - 1 copies are in flight whenever a warp waits.
+                asm volatile("" ::"r"(cur[0].q.x), "r"(cur[WSTEP - 1].q.x));   // (the loads have landed)
+                __syncwarp();
+                if (lane == 0) {
+                    if (atomicAdd(&sm.readers[st], 1u) == NT / 32 - 1) {
+                        sm.readers[st] = 0u;
+                        if (k + NSTAGE < n_steps) issue(k + NSTAGE, st);
+                    }
+                }
 #pragma unroll
                 for (int w = 0; w < WSTEP; ++w) {
                     const int t_base = (k * WSTEP + w) * TILE - mis;
@@ -703,25 +710,31 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                     const int tmin = min((int)(int16_t)(mn & 0xffffu), (int)(int16_t)(mn >> 16));
                     const int tmax = max((int)(int16_t)(mx & 0xffffu), (int)(int16_t)(mx >> 16));
                     if (t_base >= 0 && t_base + TILE <= N) {
-                        if (tmin >= wlo && tmax <= wlo + WBINS - 1) {
+                        if (tmin >= ok_lo && tmax <= ok_hi) {
 #pragma unroll
-                            for (int u = 0; u < PER; ++u) atomicAdd(col + (int)cur[w].h[u] * WCOLS, one);
+                            for (int u = 0; u < PER; ++u)
+                                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(col + (uint32_t)((int)cur[w].h[u] * (4 * WCOLS))),
+                                             "r"(one)
+                                             : "memory");
                         } else {
 #pragma unroll
                             for (int u = 0; u < PER; ++u) {
                                 const int vv = cur[w].h[u];
-                                if ((unsigned)(vv - wlo) < (unsigned)WBINS) atomicAdd(col + vv * WCOLS, one);
+                                if ((unsigned)(vv - wlo) < (unsigned)WBINS)
+                                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(col + (uint32_t)(vv * (4 * WCOLS))), "r"(one)
+                                                 : "memory");
                                 else if (vv < wlo) ++n_below;
                                 else ++n_above;
                             }
-                        }
-                        if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {   // note where Brute will patch
-                            const int g0 = t_base + tid * PER;
+                            if (p.spike_mode == 1 && (tmin < 250 || tmax > 1000)) {   // note where Brute will patch
+                                const int g0 = t_base + tid * PER;
 #pragma unroll
-                            for (int u = 0; u < PER; ++u) {
-                                if (cur[w].h[u] > 1000 || cur[w].h[u] < 250) {
-                                    const int pos = atomicAdd(&sm.n_spikes, 1);
-                                    if (pos < SPIKE_CAP) reinterpret_cast<uint32_t *>(sm.spike_key)[pos] = (uint32_t)(g0 + u);
+                                for (int u = 0; u < PER; ++u) {
+                                    if (cur[w].h[u] > 1000 || cur[w].h[u] < 250) {
+                                        const int pos = atomicAdd(&sm.n_spikes, 1);
+                                        if (pos < SPIKE_CAP)
+                                            reinterpret_cast<uint32_t *>(sm.spike_key)[pos] = (uint32_t)(g0 + u);
+                                    }
                                 }
                             }
                         }
