@@ -35,4 +35,7 @@ full mid_C4    mid_            5 5 python bench.py --locus C9ORF72_1000 --reads 
 full probe     fp64_add_probe  1 1 python bench.py --reads 5000 --steps 1 --warmup 1 $Q
 full aux       "normalize_kernel|pore_lookup|dequantize" 2 4 python scripts/bench_aux.py
 fi
+if [ "$WHAT" = aux ]; then
+full aux       normalize_kernel 2 1 env AUX_ONLY_NORM=1 python scripts/bench_aux.py
+fi
 du -sh gpurun_out

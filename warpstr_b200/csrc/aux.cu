@@ -268,9 +268,6 @@ struct NormSmem {
     double shift, scale;
 };
 constexpr int HALO = 8;
-#ifndef WSTR_NORM_EXP
-#define WSTR_NORM_EXP 0
-#endif
 #ifndef WSTR_NORM_BLOCKS
 #define WSTR_NORM_BLOCKS 3          // resident CTAs per SM (75 KB of shared memory each)
 #endif
@@ -393,9 +390,6 @@ __device__ __forceinline__ uint32_t nsmem_u32(const void *q) {
 __device__ __forceinline__ void nbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nsmem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void nbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nsmem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool nbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -510,19 +504,33 @@ __device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, co
     return ret;
 }
 
-// One CTA per read, one pass over the samples, 2048 per step.  The read is walked from the
-// 16-byte boundary at or before its first sample, so every thread loads its 8 samples with one
-// aligned 16-byte load, a step ahead of their use (samples in front of / behind the read are
+// One CTA per read (persistent: the CTAs draw reads from a queue), one pass over the samples.  The read is
+// walked from the 16-byte boundary at or before its first sample (samples in front of / behind the read are
 // masked).  Indices inside a read are 32-bit.
 //
-// Brute / None (the reference's default and its off switch) take a loop without a barrier: a
-// histogram is additive, so every thread counts its RAW samples unconditionally and only notes
-// where the out-of-range ones are; afterwards one lane walks those (sorted, typically a few tens
-// per read) in ascending order exactly like fast5.py:90-101 -- later medians see earlier fixes --
-// moves each patched sample from its old histogram bin to its new one and fixes it in the stashed
-// window.  A read with more than SPIKE_CAP such samples, and the median-filter modes (every sample
-// changes), take the tile loop: the tile in shared memory, one barrier per tile, the patching
-// done tile by tile.
+// Brute / None (the reference's default and its off switch) -- the window path.  A histogram is additive, so
+// every thread counts its RAW samples and only notes where the ones Brute will patch are; the order statistics
+// (two percentiles around the median, then the median absolute deviation) only ever look at values near the
+// median, so the histogram covers a WBINS-value window placed around the median of 32 samples spread over the
+// read and the samples outside it are merely counted (under / over).  What the scan costs is set by three things,
+// each measured (profiles/r02_summary.md, clock64 phase counters under -DWSTR_NORM_TIMING):
+//   * bytes in flight: 16-byte loads into registers are bounded by what is left of the L1 beside 3 x 72 KB of
+//     shared memory, and a rotating register queue (a = b; b = load) waits for the newest load every step; the
+//     samples therefore come by bulk asynchronous copy (TMA) into NSTAGE shared-memory stages of two tiles, a
+//     stage refilled by whichever warp is last to have taken its samples out of it;
+//   * instructions per sample: the common step (eight samples all inside the window, none to patch) is min/max
+//     two samples at a time, two compares, eight `red.shared` on precomputed 32-bit addresses; everything
+//     unusual is out of line or behind a rarely taken branch;
+//   * what happens between scans, when one warp works and seven wait: the noted samples are sorted in registers,
+//     their neighbourhoods fetched all at once, and patched lane-parallel (fast5.py:90-101: out[i] =
+//     median(out[i-2:i+3]) in index order, so only samples within two of each other depend on one another);
+//     the 32 per-lane counters of every bin are summed and prefix-summed by the CTA, the rank queries answered
+//     by warp 0 with two ballots each; the next read's offsets and window estimate are fetched by the last warp
+//     meanwhile; the output window is asked for before the statistics and divided out of registers after them.
+// A read whose statistics fall outside the window (or with more than SPIKE_CAP noted samples, or too long for
+// the 16-bit counters) is redone on the general path: the value-indexed histogram of [0, HBINS) with a global
+// one behind it.  The median-filter modes (every sample changes) take the tile loop: the tile in shared memory,
+// one barrier per tile.
 __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const NormParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NormSmem &sm = *reinterpret_cast<NormSmem *>(smem_raw);
