@@ -2,7 +2,7 @@
   compute-sanitizer --tool memcheck python scripts/sanitize_paths.py
 Covers: specialised and catch-all DP kernels (first and masked pass), the mid-stage with the pipelined fit and the
 tiled sort (one thousand-repeat read), reps_as_one, median, the three ingestion forms, a batch cut into slices and
-waves, the split-halves resident call."""
+waves, the split-halves resident call, the normalisation kernel's window path, fallback and median filter."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -46,5 +46,13 @@ for r in reads[:6]:
     raws.append(raw); wins.append((lo, hi))
 out = eng.call_raw_batch(raws, wins, aut[:6] if False else [eng.automata and a for a in batch(eng, 'HD', 6, 11)[1]], [r.reverse for r in reads[:6]])
 print('raw chain', [len(x.resc_seq) for x in out])
+# normalisation on its own: the window path, its fallback (bimodal read), a read cut off by the window, the median filter
+from warpstr_b200.normalize import normalize_windows
+r1 = (470 + 28 * rng.standard_normal(9000)).astype(np.int16)
+r1[[5, 6, 4000, 4001, 8999]] = 1500
+r2 = np.where(rng.random(7000) < 0.5, 260, 940).astype(np.int16)
+for mode in ('Brute', 'None', 'median3'):
+    o = normalize_windows([r1, r2, r1[:37]], [(100, 3000), (0, 99999), (0, 36)], mode)
+    print('normalise', mode, [len(x) for x in o])
 torch.cuda.synchronize()
 print('done')
