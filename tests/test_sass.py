@@ -78,3 +78,27 @@ def test_fill_kernel_instruction_classes(fill_sass):
     assert not any(o.startswith(('HMMA', 'UTCMMA', 'UTCHMMA', 'IMMA', 'DMMA')) for o in ops), 'tensor-core code in the DP'
     assert ops['UBLKCP'] >= 2, 'signal tiles and traceback windows are bulk async copies (TMA engine)'
     assert ops['SYNCS'] >= 4, 'mbarrier waits/arrivals expected'
+
+
+def test_normalize_kernel_stages_its_samples_with_bulk_copies(built_lib):
+    """The normalisation kernel's scan: samples arrive by bulk asynchronous copy completing on
+    mbarriers, are counted with shared-memory reductions, and the common step makes no call -- the only calls
+    in the kernel are the out-of-line general step's (window and value-indexed form)."""
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('no cuobjdump')
+    obj = os.path.join(ROOT, 'build', 'aux.cu.o')
+    if not os.path.exists(obj):
+        import __graft_entry__ as ge
+        ge.build()
+    ins = _sass(obj, 'normalize_kernel')
+    assert ins, 'normalize_kernel is not in build/aux.cu.o'
+    ops = collections.Counter(_op(t) for _, t in ins)
+    assert ops['UBLKCP'] >= 2                       # prologue + refill
+    assert any('SYNCS.PHASECHK' in t for _, t in ins) and any('SYNCS.ARRIVE' in t for _, t in ins)
+    assert ops['ATOMS'] + ops['REDS'] + sum('RED' in _op(t) for _, t in ins) >= 16
+    # the loop the stages are consumed in: from the first wait on a stage to the refill, no call in between
+    waits = [i for i, (_, t) in enumerate(ins) if 'SYNCS.PHASECHK' in t]
+    copies = [i for i, (_, t) in enumerate(ins) if _op(t) == 'UBLKCP']
+    first_wait = min(w for w in waits if w > copies[0])
+    refill = min(c for c in copies if c > first_wait)
+    assert not any(_op(t) == 'CALL' for _, t in ins[first_wait:refill])
