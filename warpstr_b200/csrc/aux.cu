@@ -135,7 +135,24 @@ __global__ void __launch_bounds__(256) pore_lookup_smem_kernel(const uint8_t *__
                 else ++n_bad;
             }
         }
-        if (i + PORE_VPT2 <= n_out) {
+        const int64_t wbase = i - (int64_t)(threadIdx.x & 31) * PORE_VPT2;   // first output of this warp's 256
+        if (wbase + 32 * PORE_VPT2 <= n_out) {
+            // The warp's 256 levels go through shared memory so that every store instruction writes 512
+            // contiguous bytes: 16-byte stores straight from the registers land 64 bytes apart, half a sector
+            // each.  Rows of 8 levels padded to 9 keep both the 8-byte writes and the reads off each other's banks.
+            double *stg = pore_tab + n_entries + (threadIdx.x >> 5) * (32 * (PORE_VPT2 + 1));
+            const int lane = threadIdx.x & 31;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < PORE_VPT2; ++j) stg[lane * (PORE_VPT2 + 1) + j] = v[j];
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < PORE_VPT2 / 2; ++jj) {
+                const int e = jj * 64 + lane * 2;                 // levels e, e + 1 of the warp's 256
+                const double *src = stg + (e >> 3) * (PORE_VPT2 + 1) + (e & 7);
+                reinterpret_cast<double2 *>(out + wbase)[jj * 32 + lane] = make_double2(src[0], src[1]);
+            }
+        } else if (i + PORE_VPT2 <= n_out) {
 #pragma unroll
             for (int j = 0; j < PORE_VPT2; j += 2)
                 reinterpret_cast<double2 *>(out + i)[j / 2] = make_double2(v[j], v[j + 1]);
@@ -159,8 +176,17 @@ extern "C" int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d
         const int n_entries = 1 << (2 * k);
         int64_t blocks2 = (n_out + (int64_t)threads * PORE_VPT2 - 1) / ((int64_t)threads * PORE_VPT2);
         if (blocks2 > 148 * 4) blocks2 = 148 * 4;
+        const size_t smem = (n_entries + (threads / 32) * 32 * (PORE_VPT2 + 1)) * sizeof(double);   // table + a staging tile per warp
+        static unsigned long long attr_done = 0ull;      // devices the function attribute is set on
+        int dev = 0;
+        WSTR_CUDA(cudaGetDevice(&dev));
+        if (!((attr_done >> (dev & 63)) & 1ull)) {
+            WSTR_CUDA(cudaFuncSetAttribute(pore_lookup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((4096 + (threads / 32) * 32 * (PORE_VPT2 + 1)) * sizeof(double))));
+            attr_done |= 1ull << (dev & 63);
+        }
         wstr_prof_begin(3, static_cast<cudaStream_t>(stream));
-        pore_lookup_smem_kernel<<<(int)blocks2, threads, n_entries * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
+        pore_lookup_smem_kernel<<<(int)blocks2, threads, smem, static_cast<cudaStream_t>(stream)>>>(
             d_seq, n, n_out, d_table, k, n_entries, d_out, d_bad);
         wstr_prof_end(static_cast<cudaStream_t>(stream));
         WSTR_CUDA(cudaGetLastError());
