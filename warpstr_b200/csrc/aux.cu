@@ -550,9 +550,9 @@ __device__ __noinline__ int norm_step_general(NormSmem &sm, const NormCtx &c, co
 //   * what happens between scans, when one warp works and seven wait: the noted samples are sorted in registers,
 //     their neighbourhoods fetched all at once, and patched lane-parallel (fast5.py:90-101: out[i] =
 //     median(out[i-2:i+3]) in index order, so only samples within two of each other depend on one another);
-//     the 32 per-lane counters of every bin are summed and prefix-summed by the CTA, the rank queries answered
-//     by warp 0 with two ballots each; the next read's offsets and window estimate are fetched by the last warp
-//     meanwhile; the output window is asked for before the statistics and divided out of registers after them.
+//     the other warps meanwhile sum the 32 per-lane counters of every bin and the last one fetches the next
+//     read's offsets and window estimate; then the prefix sums, and the rank queries answered by warp 0 with two
+//     ballots each; the output window is asked for before the statistics and divided out of registers after them.
 // A read whose statistics fall outside the window (or with more than SPIKE_CAP noted samples, or too long for
 // the 16-bit counters) is redone on the general path: the value-indexed histogram of [0, HBINS) with a global
 // one behind it.  The median-filter modes (every sample changes) take the tile loop: the tile in shared memory,
@@ -1046,8 +1046,27 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                     wreg[i] = a | b2 << 16;
                 }
             }
-            prepare_next();                                       // (the last warp; warp 0 has the patching and the statistics to do)
             uint32_t *const sidx = reinterpret_cast<uint32_t *>(sm.spike_key);   // the noted samples' indices
+            if (warp != 0) {
+                // warps 1-7, while warp 0 patches: every bin's 32 counters summed into cum[bin] and left zero.
+                // Neighbouring threads' rows start 16 banks apart, and with the 16-byte pieces taken in an order
+                // skewed by bin / 2 a quarter warp's eight accesses cover the 32 banks once.
+                static_assert(WCOLS == 16, "window reduction layout");
+                for (int bin = tid - 32; bin < WBINS; bin += NT - 32) {
+                    uint4 *row = reinterpret_cast<uint4 *>(sm.hist + bin * WCOLS);
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = (j + (bin >> 1)) & 3;
+                        const uint4 x = row[c];
+                        row[c] = make_uint4(0u, 0u, 0u, 0u);
+                        acc += (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) +
+                               (x.w & 0xffffu) + (x.w >> 16);
+                    }
+                    cum[bin] = acc;
+                }
+            }
+            prepare_next();                                       // (the last warp, meanwhile)
             if (ns > 0 && ns <= SPIKE_CAP && warp == 0) {
                 // Brute (fast5.py:90-101) on the noted samples.  Ascending order (bitonic network, +inf beyond ns) ...
                 if (ns <= 32) {                                    // one index per lane, sorted across the warp
@@ -1145,50 +1164,25 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
             }
             __syncthreads();
         WSTR_NORM_T(3);
-            // Every bin's 32 counters (and Brute's corrections) summed and left zero, then inclusive prefix sums over
-            // the bins.  Thread t takes bins t and t + NT: neighbouring threads' rows start 16 banks apart, and with
-            // the 16-byte pieces taken in an order skewed by t / 2 a quarter warp's eight accesses cover the 32 banks once.
-            static_assert(WBINS == 2 * NT && WCOLS == 16, "window reduction layout");
-            uint32_t sb[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int bin = tid + q * NT;
-                uint4 *row = reinterpret_cast<uint4 *>(sm.hist + bin * WCOLS);
-                uint32_t acc = (uint32_t)sm.corr[bin];
-                sm.corr[bin] = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = (j + (tid >> 1)) & 3;
-                    const uint4 x = row[c];
-                    row[c] = make_uint4(0u, 0u, 0u, 0u);
-                    acc += (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) +
-                           (x.w & 0xffffu) + (x.w >> 16);
-                }
-                sb[q] = acc;
-            }
-            uint32_t inc0 = sb[0], inc1 = sb[1];
+            // Brute's corrections added, inclusive prefix sums over the bins: two adjacent bins per thread
+            static_assert(WBINS == 2 * NT, "window prefix layout");
+            const uint32_t v0 = cum[2 * tid] + (uint32_t)sm.corr[2 * tid];
+            const uint32_t v1 = cum[2 * tid + 1] + (uint32_t)sm.corr[2 * tid + 1];
+            sm.corr[2 * tid] = 0;
+            sm.corr[2 * tid + 1] = 0;
+            uint32_t inc = v0 + v1;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
-                if (lane >= o) {
-                    inc0 += t0;
-                    inc1 += t1;
-                }
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
             }
-            if (lane == 31) {                                     // (the bitmap is free between reads: 2 x 8 warp totals)
-                sm.spike_bits[warp] = inc0;
-                sm.spike_bits[8 + warp] = inc1;
-            }
+            if (lane == 31) sm.spike_bits[warp] = inc;            // (the bitmap is free between reads: 8 warp totals)
             __syncthreads();
             {
-                uint32_t base0 = inc0, base1 = inc1;
-                for (int w = 0; w < NT / 32; ++w) {
-                    if (w < warp) base0 += sm.spike_bits[w];
-                    base1 += sm.spike_bits[w];                    // all of the first half comes before the second
-                    if (w < warp) base1 += sm.spike_bits[8 + w];
-                }
-                cum[tid] = base0;
-                cum[NT + tid] = base1;
+                uint32_t base = inc - (v0 + v1);
+                for (int w = 0; w < warp; ++w) base += sm.spike_bits[w];
+                cum[2 * tid] = base + v0;
+                cum[2 * tid + 1] = base + v0 + v1;
             }
             __syncthreads();
         WSTR_NORM_T(4);
@@ -1197,33 +1191,46 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                 // Order statistics by the whole warp: a monotone predicate over the bins is located with two
                 // ballots (the lanes' block ends, then the block's bins).  Every rank query has to fall inside the
                 // window; one that does not sends the read to the general path below.
-                const int64_t below = sm.below;
-                const int64_t inside = cum[WBINS - 1];
+                // (N <= WIN_MAX_N: every count and rank fits 32 bits)
+                const int below = sm.below;
+                const int inside = (int)cum[WBINS - 1];
                 bool ok = true;                                   // (warp-uniform throughout)
-                auto wcum = [&](int v) -> int64_t {               // samples <= v, for v in [wlo - 1, wlo + WBINS)
-                    return v < wlo ? below : below + (int64_t)cum[v - wlo];
+                auto wcum = [&](int v) -> int {                   // samples <= v, for v in [wlo - 1, wlo + WBINS)
+                    return v < wlo ? below : below + (int)cum[v - wlo];
                 };
-                auto value_at = [&](int64_t rank) -> int {        // smallest v with (samples <= v) > rank
+                auto value_at = [&](int rank) -> int {            // smallest v with (samples <= v) > rank
                     if (rank < below || rank >= below + inside) {
                         ok = false;
                         return 0;
                     }
                     constexpr int B = WBINS / 32;
-                    const bool e1 = below + (int64_t)cum[lane * B + B - 1] > rank;
+                    const bool e1 = below + (int)cum[lane * B + B - 1] > rank;
                     const int L = __ffs(__ballot_sync(0xffffffffu, e1)) - 1;
-                    const bool e2 = lane < B && below + (int64_t)cum[L * B + min(lane, B - 1)] > rank;
+                    const bool e2 = lane < B && below + (int)cum[L * B + min(lane, B - 1)] > rank;
                     const int q = __ffs(__ballot_sync(0xffffffffu, e2)) - 1;
                     return wlo + L * B + q;
                 };
-                const double p0 = percentile_from(value_at, 46.5 / 100.0);
-                const double p1 = percentile_from(value_at, 53.5 / 100.0);
+                auto percentile32 = [&](double q) {               // percentile_from with 32-bit indices: same doubles
+                    const double vidx = (double)(N - 1) * q;
+                    int i0 = (int)floor(vidx), i1 = i0 + 1;
+                    if (vidx >= (double)(N - 1)) i0 = i1 = N - 1;
+                    const double gamma = vidx - (double)i0;
+                    const int a = value_at(i0);
+                    const int b2 = value_at(i1);
+                    const double diff = (double)(int16_t)(b2 - a);   // numpy subtracts in int16
+                    double res = (double)a + diff * gamma;
+                    if (gamma >= 0.5) res = (double)b2 - diff * (1.0 - gamma);
+                    return res;
+                };
+                const double p0 = percentile32(46.5 / 100.0);
+                const double p1 = percentile32(53.5 / 100.0);
                 const double shift = (p0 + p1) / 2.0;
                 const int fl = (int)floor(shift);
                 // values by |v - shift|: the pairs (fl - m, fl + 1 + m), m = 0, 1, ...; the first m pairs hold the
                 // samples in [fl - m + 1, fl + m].  m_max: the last pair inside the window
                 const int m_max = ok ? min(fl - wlo, wlo + WBINS - 2 - fl) : -1;
-                auto pairs = [&](int m) -> int64_t { return wcum(fl + m + 1) - wcum(fl - m - 1); };
-                auto absdev_at = [&](int64_t rank) -> double {
+                auto pairs = [&](int m) -> int { return wcum(fl + m + 1) - wcum(fl - m - 1); };
+                auto absdev_at = [&](int rank) -> double {
                     if (m_max < 0 || pairs(m_max) <= rank) {
                         ok = false;
                         return 0.0;
@@ -1234,11 +1241,11 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                     const int mq = L * B + lane;
                     const bool e2 = lane < B && mq <= m_max && pairs(min(mq, m_max)) > rank;
                     const int mm = L * B + __ffs(__ballot_sync(0xffffffffu, e2)) - 1;
-                    const int64_t before = wcum(fl + mm) - wcum(fl - mm);
-                    const int64_t scl = wcum(fl - mm) - wcum(fl - mm - 1);
-                    const int64_t sch = wcum(fl + 1 + mm) - wcum(fl + mm);
+                    const int before = wcum(fl + mm) - wcum(fl - mm);
+                    const int scl = wcum(fl - mm) - wcum(fl - mm - 1);
+                    const int sch = wcum(fl + 1 + mm) - wcum(fl + mm);
                     const double dl = fabs((double)(fl - mm) - shift), du = fabs((double)(fl + 1 + mm) - shift);
-                    const int64_t within = rank - before;
+                    const int within = rank - before;
                     if (dl <= du) return within < scl ? dl : du;  // inside the pair the nearer value first
                     return within < sch ? du : dl;
                 };
