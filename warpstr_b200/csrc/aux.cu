@@ -1383,6 +1383,15 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
         __syncthreads();
         WSTR_NORM_T(5);
         const double shift = sm.shift, scale = sm.scale;
+        // (x - shift) / scale, the reference's expression (fast5.py:113).  The divisor is the same for the whole
+        // read: the five-instruction exact division of wstr_internal.h (the very bits of a / d) where its
+        // ranges hold -- the numerator is 0 or a multiple of ulp(shift) below 2^17 -- and the plain one otherwise
+        // (scale 0, a constant read).
+        const Divisor dv = make_divisor(scale);
+        auto normalised = [&](int v) {
+            const double a = (double)v - shift;
+            return dv.fast ? div_fast(a, dv) : a / scale;
+        };
 
         if (done) {
             // window path: straight from the read, then the patched samples the window holds
@@ -1390,20 +1399,20 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
 #pragma unroll
                 for (int i = 0; i < WREG; ++i) {                 // (the quotients unconditionally: independent chains)
                     const int t0 = tid + (2 * i) * NT, t1 = t0 + NT;
-                    const double q0 = ((double)(int16_t)(wreg[i] & 0xffffu) - shift) / scale;
-                    const double q1 = ((double)(int16_t)(wreg[i] >> 16) - shift) / scale;
+                    const double q0 = normalised((int16_t)(wreg[i] & 0xffffu));
+                    const double q1 = normalised((int16_t)(wreg[i] >> 16));
                     if (t0 < Tw) out[t0] = q0;
                     if (t1 < Tw) out[t1] = q1;
                 }
             } else {
-                for (int t = tid; t < Tw; t += NT) out[t] = ((double)raw[lo + t] - shift) / scale;
+                for (int t = tid; t < Tw; t += NT) out[t] = normalised(raw[lo + t]);
             }
             if (win_ns > 0) {
                 __syncthreads();
                 const uint32_t *const sidx = reinterpret_cast<const uint32_t *>(sm.spike_key);
                 for (int t = tid; t < win_ns; t += NT) {
                     const int i = (int)sidx[t];
-                    if (i >= lo && i - lo < Tw) out[i - lo] = ((double)sm.spike_nv[t] - shift) / scale;
+                    if (i >= lo && i - lo < Tw) out[i - lo] = normalised(sm.spike_nv[t]);
                 }
             }
         } else {
@@ -1412,7 +1421,7 @@ __global__ void __launch_bounds__(NT, WSTR_NORM_BLOCKS) normalize_kernel(const N
                 const int len = (int)min((int64_t)TILE, Tw - t0);
                 for (int t = tid; t < len; t += NT) sm.tile[HALO + t] = stash[t0 + t];
                 __syncthreads();
-                for (int t = tid; t < len; t += NT) out[t0 + t] = ((double)sm.tile[HALO + t] - shift) / scale;
+                for (int t = tid; t < len; t += NT) out[t0 + t] = normalised(sm.tile[HALO + t]);
                 __syncthreads();
             }
         }

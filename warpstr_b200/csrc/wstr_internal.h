@@ -164,3 +164,39 @@ int wstr_launch_fill(int kc, int kg, int deg, int mv, const FillParams &p, cudaS
 // catch-all (dtw_any.cu): any min_values_per_state, any in-degree; spad_max = widest automaton of the launch
 int wstr_launch_fill_any(int mv, int spad_max, const FillParams &p, cudaStream_t s);
 size_t wstr_any_smem_bytes(int mv, int spad_max);
+
+#ifdef __CUDACC__
+// ---- exact division by a divisor that is used many times -------------------------------------------
+// The spline basis divides by (xe - xb) six times per evaluated sample, the t statistic by 3.0 five times per
+// position, the normalisation by the read's scale once per window sample; a double division is ~15 FP64-pipe instructions on this GPU.  With
+// y = RN(1/d) taken once (one IEEE division),
+//     q0 = RN(a*y);  r0 = a - q0*d (exact, one FMA);  q1 = RN(q0 + r0*y);
+//     r1 = a - q1*d (exact);                          q  = RN(q1 + r1*y)
+// is the correctly rounded a/d (Markstein 1990: one such step on a faithful q with a correctly
+// rounded reciprocal rounds correctly; the first step makes q1 faithful), i.e. the very bits
+// `a / d` gives, in 5 instructions.  Used only where nothing can over- or underflow: |d| within
+// 2^+-60 and the numerator zero or within 2^+-600, established per call (GUARD), per sample or per
+// read (`tame`); every other operand takes the plain division.  The identity is also checked on
+// the host against a/d (oracle/div_identity.c: 4e9 operand pairs over those ranges, adversarial
+// significands included -- divisor all ones / a power of two / 1.5 -- no mismatch).
+struct Divisor {
+    double d, y;
+    bool fast;     // 2^-60 <= |d| <= 2^60
+};
+__device__ __forceinline__ Divisor make_divisor(double d) {
+    Divisor r;
+    r.d = d;
+    r.y = 1.0 / d;
+    const unsigned e = (static_cast<unsigned>(__double2hiint(d)) >> 20) & 0x7ffu;
+    r.fast = e - (1023u - 60u) <= 120u;
+    return r;
+}
+// the five-instruction form; the caller vouches for the operand ranges
+__device__ __forceinline__ double div_fast(double a, const Divisor &dv) {
+    const double q0 = __dmul_rn(a, dv.y);
+    const double r0 = __fma_rn(-q0, dv.d, a);
+    const double q1 = __fma_rn(r0, dv.y, q0);
+    const double r1 = __fma_rn(-q1, dv.d, a);
+    return __fma_rn(r1, dv.y, q1);
+}
+#endif
