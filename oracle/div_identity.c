@@ -1,9 +1,9 @@
 /* Test infrastructure (not product code): checks on the host the identity the mid-stage kernels
- * rely on (warpstr_b200/csrc/midstage.cu, div_fast): with y = RN(1/d),
+ * rely on (warpstr_b200/csrc/wstr_internal.h, div_fast: the mid-stage kernels and the normalisation kernel): with y = RN(1/d),
  *     q0 = RN(a*y); r0 = fma(-q0, d, a); q1 = fma(r0, y, q0); r1 = fma(-q1, d, a); q = fma(r1, y, q1)
  * equals the IEEE quotient a/d bit for bit (Markstein's correction step applied twice).  Operands: random
  * significands plus adversarial ones (divisor all ones / a power of two / 1.5 = the division by 3),
- * exponents inside the range the kernels allow.  Prints the mismatch counts of the one- and two-step forms.
+ * exponents inside the range the kernels allow; and the normalisation kernel's (sample - shift) / scale.  Prints the mismatch counts of the one- and two-step forms.
  * Build: gcc -O2 -mfma -ffp-contract=off -o div_identity div_identity.c -lm ; run: ./div_identity [pairs] */
 #include <math.h>
 #include <stdint.h>
@@ -39,6 +39,15 @@ int main(int argc, char **argv) {
         if (mode == 5) md = 0x8000000000000ull;             /* 1.5 * 2^e: the divisions by 3 */
         const int ea = (int)((ee >> 8) % 1201) - 600, ed = (int)((ee >> 24) % 121) - 60;
         volatile double a = make(ma, ea, (int)((ee >> 40) & 1)), d = make(md, ed, (int)((ee >> 41) & 1));
+        if (mode == 6 || mode == 7) {
+            /* the normalisation kernel's operands (aux.cu): (x - shift) / scale, x an int16 sample, shift a
+             * mean of two interpolated percentiles, scale a median absolute deviation: an integer, a half, or
+             * (mode 7) anything of that size */
+            const double shift = (double)(int)(ma % 2048) + (mode == 6 ? (double)((ma >> 16) % 4) * 0.25 : make(ma >> 12, -1, 0) - 0.5);
+            const double scale = mode == 6 ? (double)(1 + (int)(md % 400)) * 0.5 : make(md, (int)(md % 9), 0);
+            a = (double)(int)((ee >> 44) % 65536 - 32768) - shift;
+            d = scale;
+        }
         const double y = 1.0 / d, ref = a / d;
         const double q0 = a * y;
         const double r0 = fma(-q0, d, a);

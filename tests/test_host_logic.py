@@ -184,9 +184,10 @@ def test_synthetic_batch_generator_is_consistent():
 
 
 def test_exact_division_identity_the_midstage_relies_on(tmp_path):
-    """csrc/midstage.cu divides by repeated divisors with y = RN(1/d) and two FMA correction steps;
-    oracle/div_identity.c checks on the host that this gives the bits of a/d (random and adversarial
-    significands, the kernels' exponent ranges).  Needs gcc and a CPU with FMA."""
+    """The mid-stage and the normalisation kernel divide by repeated divisors with y = RN(1/d) and two FMA
+    correction steps (csrc/wstr_internal.h); oracle/div_identity.c checks on the host that this gives the bits
+    of a/d (random and adversarial significands, the kernels' exponent ranges, and the normalisation's
+    (sample - shift) / scale family).  Needs gcc and a CPU with FMA."""
     import os
     import shutil
     import subprocess

@@ -177,7 +177,7 @@ size_t wstr_any_smem_bytes(int mv, int spad_max);
 // `a / d` gives, in 5 instructions.  Used only where nothing can over- or underflow: |d| within
 // 2^+-60 and the numerator zero or within 2^+-600, established per call (GUARD), per sample or per
 // read (`tame`); every other operand takes the plain division.  The identity is also checked on
-// the host against a/d (oracle/div_identity.c: 4e9 operand pairs over those ranges, adversarial
+// the host against a/d (oracle/div_identity.c: 4e9 operand pairs over those ranges, the normalisation's operands and adversarial
 // significands included -- divisor all ones / a power of two / 1.5 -- no mismatch).
 struct Divisor {
     double d, y;
