@@ -65,7 +65,10 @@ int wstr_pore_lookup(const uint8_t *d_seq, int64_t n, const double *d_table, int
  * spike_mode: 0 None, 1 Brute, 3 median3, 5 median5;
  * window [win_lo[r], win_hi[r]] (inclusive, as in the reference) is written to
  * d_out + out_off[r] as float64.  d_shift_scale (optional, may be NULL) receives
- * {shift, scale} per read.  d_workspace: wstr_normalize_workspace_bytes(n_reads) bytes. */
+ * {shift, scale} per read.  d_workspace: wstr_normalize_workspace_bytes(n_reads) bytes.
+ * The samples are fetched in whole 16-byte words: if d_raw's first or last sample is not 16-byte
+ * aligned, up to 14 bytes in front of / behind the buffer are read (and ignored) -- inside the
+ * allocation granule for a cudaMalloc'd or torch buffer. */
 int64_t wstr_normalize_workspace_bytes(int32_t n_reads);
 int wstr_normalize_batch(const int16_t *d_raw, const int64_t *raw_off, const int32_t *win_lo,
                          const int32_t *win_hi, int32_t n_reads, int32_t spike_mode,
